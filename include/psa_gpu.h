@@ -1,0 +1,116 @@
+/* psa_gpu.h -- C ABI of libpsagpu.so: B200-native resolvent-norm grid kernel for Pseudospectra.jl.
+ *
+ * This is the drop-in boundary for ONE call of the reference: the per-batch core
+ *     psacore(T, S, q0, x, y, bw; tol, ...) -> (Z, algo, warned)        /root/reference/src/compute.jl:448-617
+ * as invoked from the dense row loop of psa_compute (src/compute.jl:199-219).  A Julia `ccall` shim
+ * (julia/PseudospectraGPU.jl, shown in INTEGRATION.md) replaces that loop when opts[:gpu] is set and keeps
+ * everything before (options, grid, projection: compute.jl:94-153) and after (mirror, clamp, levels:
+ * compute.jl:222-267) unchanged.
+ *
+ * Conventions: plain pointers and sizes only; all matrices column-major like Julia's; complex numbers are
+ * interleaved (re, im) doubles (`ComplexF64` / `double _Complex`).  Every function returns an int status
+ * (0 = ok, < 0 = error, see psa_gpu_strerror); no C++ exception crosses this boundary.  Host pointers are
+ * never retained after a call returns.  A context is not re-entrant.  There is NO CPU fallback: every entry
+ * point fails with PSA_ERR_CUDA / PSA_ERR_NODEVICE when no sm_100 device is usable.
+ */
+#ifndef PSA_GPU_H
+#define PSA_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes */
+#define PSA_OK 0
+#define PSA_ERR_ARG (-1)         /* bad argument (null pointer, m < n, sizes <= 0, ...) */
+#define PSA_ERR_CUDA (-2)        /* CUDA runtime / launch failure; text via psa_gpu_last_error */
+#define PSA_ERR_CANCELLED (-3)   /* *cancel became 1: mirrors `info = -3` / `return nothing` (compute.jl:83,202-204) */
+#define PSA_ERR_UNSUPPORTED (-4) /* shape the GPU path does not cover: the shim falls through to the Julia code */
+#define PSA_ERR_NODEVICE (-5)    /* no CUDA device / not sm_100 */
+#define PSA_ERR_NOMATRIX (-6)    /* psa_gpu_grid before psa_gpu_set_matrix */
+#define PSA_ERR_NCCL (-7)        /* multi-GPU transport failure */
+#define PSA_ERR_NOMEM (-8)       /* device allocation failed */
+
+/* algorithm actually used, mirrors the `algo` Symbol psacore returns (compute.jl:535,580,594) */
+#define PSA_ALGO_NONE 0
+#define PSA_ALGO_SQ_LANC 1 /* :sq_lanc -- square upper-triangular T, m == n >= minlancs4psa (55)     */
+#define PSA_ALGO_HESSQR 2  /* :HessQR  -- rectangular Hessenberg, bw == 2 and m > maxstdqr4hess (200) */
+
+/* indices into the counts[] array returned by psa_gpu_grid */
+#define PSA_COUNT_NONCONVERGED 0 /* points where Lanczos hit maxit: shim raises the warning of compute.jl:603-606 */
+#define PSA_COUNT_EIGFAIL 1      /* points with the bigsigma fallback (non-finite recurrence): warning of compute.jl:607-610 */
+#define PSA_COUNT_TOTAL_ITERS 2  /* sum over points of Lanczos iterations (flop accounting: 8 n^2 per iteration) */
+#define PSA_COUNT_POINTS 3       /* points computed */
+#define PSA_NCOUNTS 4
+
+/* indices into the stats[] array of psa_gpu_last_stats */
+#define PSA_STAT_SOLVE_MS 0      /* device time spent in the dominant kernel (CUDA events on the launching stream) */
+#define PSA_STAT_SOLVE_LAUNCHES 1
+#define PSA_STAT_TOTAL_LAUNCHES 2 /* all kernels launched by the last grid call */
+#define PSA_STAT_GRID_MS 3       /* device time of the whole grid call, first launch to last */
+#define PSA_STAT_TICKS 4         /* scheduler ticks (one Lanczos iteration of every active shift per tick) */
+#define PSA_STAT_FLOPS 5         /* algorithmic real FP64 flops of the last call: 8 n^2 sum(iters) (+ QR for HessQR) */
+#define PSA_STAT_BYTES 6         /* algorithmic bytes for the HBM-bound HessQR path, 0 for sq_lanc */
+#define PSA_STAT_PACK_MS 7       /* device time of the one-time T packing in the last set_matrix */
+#define PSA_NSTATS 8
+
+/* Create a context driving `ngpus` devices from this process (devices 0..ngpus-1, or device_ids[0..ngpus-1]
+ * when device_ids is non-null).  With ngpus > 1 the grid rows are sharded cyclically over the devices
+ * (SURVEY §8e); T is replicated by NCCL broadcast.  A one-process-per-GPU host (bench.py under torchrun)
+ * uses ngpus = 1 per rank and shards rows itself. */
+int psa_gpu_init(int ngpus, const int* device_ids, void** ctx);
+
+/* Upload the (decomposed) matrix and pre-pack it for the kernels; it stays device-resident until the next
+ * set_matrix / free so that zoom re-computations (src/zooming.jl) reuse it.
+ *   m == n : T is upper triangular (`UpperTriangular{ComplexF64}` parent array); only i <= j is read, exactly
+ *            as `UpperTriangular` ignores the strict lower part (compute.jl:600).                 -> :sq_lanc
+ *   m == n+1, m > 200 : rectangular Hessenberg (xeigs.jl:226), lower bandwidth 2.                  -> :HessQR
+ *   anything else (n < 55 SVD branch, rect_qr, generalised S != I) -> PSA_ERR_UNSUPPORTED.
+ * T: column-major, leading dimension ldt (>= m), interleaved complex128. */
+int psa_gpu_set_matrix(void* ctx, const double* T, int64_t ldt, int m, int n);
+
+/* Device-resident variant: d_T is a device pointer on the context's first device (same layout). */
+int psa_gpu_set_matrix_device(void* ctx, const double* d_T, int64_t ldt, int m, int n);
+
+/* The psacore replacement.  For every grid point z = x[k] + i*y[j] computes sigma_max of
+ * (T-z)^{-1}(T-z)^{-H} by the inverse-Lanczos recurrence of `_psa_lanczos!` (compute.jl:619-665) started from
+ * q0 (unit norm, length >= n; the same vector for every point, compute.jl:207-210,622) and returns
+ * Z[j + k*ly] = 1/sqrt(sigma) (compute.jl:611), column-major ly x lx.
+ *   tol, maxit, bigsigma : psatol (1e-5), thresholds.maxit_lancs (99), 0.1*floatmax (compute.jl:88,27,475)
+ *   iters  : nullable, ly x lx int32, Lanczos iterations per point
+ *   counts : nullable, PSA_NCOUNTS int64 (see PSA_COUNT_*)
+ *   cancel : nullable; polled between scheduler ticks; *cancel == 1 -> PSA_ERR_CANCELLED (compute.jl:202-204)
+ * Returns the algorithm used (PSA_ALGO_*) through *algo when non-null. */
+int psa_gpu_grid(void* ctx, const double* x, int lx, const double* y, int ly, const double* q0, double tol,
+                 int maxit, double bigsigma, double* Z, int32_t* iters, int64_t* counts, int* algo,
+                 volatile int* cancel);
+
+/* Same computation with every array already resident in device memory of the context's first device
+ * (single-device contexts only): d_x[lx], d_y[ly], d_q0[2n], d_Z[ly*lx], d_iters[ly*lx] (nullable).
+ * counts stays a host pointer.  Used to time the path without host<->device traffic. */
+int psa_gpu_grid_device(void* ctx, const double* d_x, int lx, const double* d_y, int ly, const double* d_q0,
+                        double tol, int maxit, double bigsigma, double* d_Z, int32_t* d_iters, int64_t* counts,
+                        int* algo, volatile int* cancel);
+
+/* Diagnostic hook used by the parity tests: v_s = (T - z_s I)^{-1} (T - z_s I)^{-H} q_s for ns shifts
+ * (one application of the operator at compute.jl:630, through the same solve kernel the grid uses).
+ * z: ns interleaved complex; Q, V: ns vectors of n interleaved complex each (vector s at offset s*n). */
+int psa_gpu_apply_resolvent(void* ctx, const double* z, int ns, const double* Q, double* V);
+
+/* Timing / accounting of the last psa_gpu_grid* call (PSA_STAT_*), device 0 of the context. */
+int psa_gpu_last_stats(void* ctx, double* stats);
+
+int psa_gpu_free(void* ctx);
+
+const char* psa_gpu_strerror(int status);
+/* Text of the last CUDA / NCCL error seen by this context (empty string if none). */
+const char* psa_gpu_last_error(void* ctx);
+/* "psagpu <version> sm_100a" */
+const char* psa_gpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSA_GPU_H */

@@ -1,0 +1,218 @@
+"""Host-side mirror of the reference interface for the hot path: `psacore` and the dense branch of
+`psa_compute` (/root/reference/src/compute.jl:87-268, 448-617), with the per-point work done by libpsagpu.
+
+Same names, argument meaning and error behaviour as the reference; the differences the GPU option implies
+ are: one start vector q for the whole grid instead of one per row batch (compute.jl:206-208), and
+all rows handed to the library in a single call.  No CPU fallback: shapes the library does not cover raise
+PsaGpuUnsupported (the Julia shim falls through to the stock code there)."""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from ._lib import PsaGpu, PsaGpuCancelled
+
+_FLOATMAX = float(np.finfo(np.float64).max)
+_FLOATMIN = float(np.finfo(np.float64).tiny)
+_SMALL_SIGMA = 1e-150  # src/Pseudospectra.jl:46
+
+
+@dataclass
+class ComputeThresholds:  # src/compute.jl:20-27
+    minlancs4psa: int = 55
+    maxstdqr4hess: int = 200
+    minnev: int = 20
+    maxit_lancs: int = 99
+
+
+_default_thresholds = ComputeThresholds()
+_ctx_cache: dict = {}
+
+
+def _context(ngpus: int) -> PsaGpu:
+    ctx = _ctx_cache.get(ngpus)
+    if ctx is None:
+        ctx = _ctx_cache[ngpus] = PsaGpu(ngpus)
+    return ctx
+
+
+def psacore(T, S, q0, x, y, bw, *, tol=1e-5, threaded=False, nt=None, warned=None, thresholds=_default_thresholds,
+            ngpus=1, ctx: PsaGpu | None = None, want_iters=False, cancel=None, resident=False):
+    """psacore(T,S,q,x,y,bw;tol) -> (Z, algo, warned)      [src/compute.jl:448-617]
+
+    T: m x n (upper-triangular square, or (n+1) x n Hessenberg with bw == 2); S must be None / identity
+    (generalised problems are not on the GPU path); q0: unit start vector (length >= n); x, y: grid lines.
+    `threaded`/`nt` are accepted for signature parity and ignored.  `warned` carries the two once-only
+    warning flags of compute.jl:603-610.  With resident=True the matrix of `ctx` is reused (zoom recompute)."""
+    if S is not None and not (np.isscalar(S) and S == 1):
+        raise NotImplementedError("generalised problems (S != I) stay on the host path")
+    warned = list(warned) if warned is not None else [False, False]
+    T = np.asarray(T)
+    m, n = T.shape
+    if m < n:
+        raise ValueError("Matrix size must be m x n with m >= n")  # compute.jl:459-461
+    if m != n and bw != 2:
+        raise NotImplementedError("rectangular non-Hessenberg input (rect_qr) is not on the GPU path")
+    own = ctx is None
+    if own:
+        ctx = _context(ngpus)
+    if not (resident and ctx.shape == (m, n)):
+        ctx.set_matrix(T)
+    Z, iters, counts, algo = ctx.grid(x, y, q0, tol=tol, maxit=thresholds.maxit_lancs, bigsigma=0.1 * _FLOATMAX,
+                                      want_iters=want_iters, cancel=cancel)
+    if counts[0] > 0 and not warned[0]:
+        import warnings
+        warnings.warn("Lanczos convergence failure(s) while computing resolvent norms")  # compute.jl:604
+        warned[0] = True
+    if counts[1] > 0 and not warned[1]:
+        import warnings
+        warnings.warn("Eigenvalue convergence failure(s) while computing resolvent norms")  # compute.jl:608
+        warned[1] = True
+    if want_iters:
+        return Z, algo, warned, iters
+    return Z, algo, warned
+
+
+# ---- grid / post-processing host logic (cheap; stays on the host exactly as in the reference) ----------
+
+def _range(a, b, n):
+    return np.linspace(float(a), float(b), int(n))
+
+
+def shift_axes(ax, npts):
+    """src/utils.jl:112-141"""
+    a3, a4 = float(ax[2]), float(ax[3])
+    if a4 > -a3:
+        tpts = int(math.floor((a4 / (a4 - a3)) * npts))
+        y = _range(a4 / (2 * (tpts - 1) + 1), a4, tpts)
+        cnt = int(np.count_nonzero(y < -a3))
+        if abs(y[min(len(y), cnt + 1) - 1] + a3) > 1e-15:
+            y = np.concatenate([y[:cnt], [-a3], y[cnt:]])
+        return y, cnt + 1
+    if a4 < -a3:
+        bpts = int(math.floor((a3 / (a3 - a4)) * npts))
+        y = _range(a3, a3 / (2 * (bpts - 1) + 1), bpts)
+        cnt = int(np.count_nonzero(y < -a4))
+        if abs(y[max(1, cnt) - 1] + a4) > 1e-15:
+            y = np.concatenate([y[:cnt], [-a4], y[cnt:]])
+        return y, -(len(y) - cnt)
+    if npts % 2 == 1:
+        return _range(0.0, a4, int(round((npts + 1) / 2))), ((npts + 1) >> 1) - 1
+    step = (a4 - a3) / npts
+    return _range(step / 2, a4, int(round(npts / 2))), npts >> 1
+
+
+def _grid(ax, npts, real_matrix, scale_equal):
+    """src/compute.jl:122-145"""
+    x_npts = y_npts = npts
+    if scale_equal:
+        y_dist, x_dist = ax[3] - ax[2], ax[1] - ax[0]
+        if x_dist > y_dist:
+            y_npts = max(5, int(math.ceil(y_dist / x_dist * npts)))
+        else:
+            x_npts = max(5, int(math.ceil(x_dist / y_dist * npts)))
+    if real_matrix and ax[3] > 0 and ax[2] < 0:
+        y, n_mirror = shift_axes(ax, y_npts)
+    else:
+        y, n_mirror = _range(ax[2], ax[3], y_npts), 0
+    return _range(ax[0], ax[1], x_npts), np.asarray(y, dtype=np.float64), n_mirror
+
+
+def _unmirror(Z, y, n_mirror):
+    """src/compute.jl:222-235"""
+    if n_mirror < 0:
+        k = -n_mirror
+        return np.vstack([Z, Z[Z.shape[0] - k:][::-1]]), np.concatenate([y, -y[len(y) - k:][::-1]])
+    if y[0] != 0:
+        return np.vstack([Z[:n_mirror][::-1], Z]), np.concatenate([-y[:n_mirror][::-1], y])
+    return np.vstack([Z[1:n_mirror + 1][::-1], Z]), np.concatenate([-y[1:n_mirror + 1][::-1], y])
+
+
+def recalc_levels(sigmin, ax):
+    """src/utils.jl:21-73"""
+    smin, smax = float(np.min(sigmin)), float(np.max(sigmin))
+    if smax <= _SMALL_SIGMA:
+        return np.zeros(0), -2
+    if smin <= _SMALL_SIGMA:
+        smin = float(np.min(sigmin[sigmin >= _SMALL_SIGMA]))
+    max_val, min_val = math.log10(smax), math.log10(smin)
+    num_lines = 8
+    last_lev = math.log10(0.03 * min(ax[3] - ax[2], ax[1] - ax[0]))
+    if max_val >= last_lev:
+        num_lines = int(math.ceil(num_lines * (last_lev - min_val) / (max_val - min_val)))
+        max_val = last_lev
+    if max_val < min_val:
+        max_val = math.log10(smin) + 0.1 * math.log10(smax / smin)
+        num_lines = 3
+    levels = np.zeros(0)
+    if num_lines > 0:
+        rnd = lambda v: float(np.round(v))
+        stepsize = max(rnd((max_val - min_val) / num_lines * 4) / 4, 0.25)
+        if stepsize >= 0.75:
+            stepsize = 1.0
+        if (max_val - min_val) / stepsize < num_lines:
+            stepsize = max(rnd((max_val - min_val) / num_lines * 10) / 10, 0.1)
+            if stepsize == 0.3:
+                stepsize = 0.2
+            elif stepsize == 0.4 or 0.6 <= stepsize <= 0.8:
+                stepsize = 0.5
+            elif stepsize >= 0.9:
+                stepsize = 1.0
+        if (max_val - min_val) / stepsize < math.ceil(num_lines / 2):
+            stepsize = (max_val - min_val) / num_lines
+        else:
+            min_val = math.ceil(min_val / stepsize) * stepsize
+            max_val = math.floor(max_val / stepsize) * stepsize
+        if stepsize > 0:
+            levels = min_val + stepsize * np.arange(int(math.floor((max_val - min_val) / stepsize + 1e-12)) + 1)
+        else:
+            levels = np.array([min_val, max_val])
+    stride = max(len(levels) // 9, 1)
+    levels = levels[::-1][::stride][::-1]
+    if len(levels) == 1:
+        levels = levels * np.ones(2)
+    return levels, 0
+
+
+def psa_compute(Targ, npts, ax, eigA, opts=None, S=None, *, psatol=1e-5, thresholds=_default_thresholds,
+                ctrlflag=None, q0=None, rng=None, ngpus=1, ctx: PsaGpu | None = None):
+    """psa_compute(T,npts,ax,eigA,opts,S=I) -> (Z,x,y,levels,info,Tproj,eigAproj,algo)   [src/compute.jl:87-268]
+
+    Dense branch with the GPU option switched on.  `opts` keys honoured: levels, recompute_levels, real_matrix,
+    scale_equal (proj_lev must be inf: projection is a host pre-step outside this path).  `ctrlflag` is a
+    one-element int32 numpy array; setting it to 1 cancels and returns None like compute.jl:202-204.
+    `q0`/`rng` supply the start vector the reference draws with randn (compute.jl:207-208)."""
+    opts = dict(opts or {})
+    Targ = np.asarray(Targ)
+    m, n = Targ.shape
+    if opts.get("proj_lev", math.inf) != math.inf:
+        raise NotImplementedError("projection (_maybe_project) is a host pre-step outside the GPU path")
+    levels = opts.get("levels")
+    re_calc = opts.get("recompute_levels", levels is None)
+    if levels is None:
+        levels = np.arange(-8, 0)
+    elif np.ndim(levels) == 0 or len(levels) == 1:
+        levels = np.ravel(levels)[0] * np.ones(2)
+    ax = [float(a) for a in ax]
+    real_matrix = opts.get("real_matrix", not np.iscomplexobj(Targ))
+    x, y, n_mirror = _grid(ax, npts, real_matrix, opts.get("scale_equal", False))
+    if q0 is None:
+        rng = rng or np.random.default_rng()
+        q0 = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        q0 = q0 / np.linalg.norm(q0)
+    try:
+        Z, algo, _ = psacore(Targ, S, q0, x, y, m - n + 1, tol=psatol, thresholds=thresholds, ngpus=ngpus, ctx=ctx,
+                             cancel=ctrlflag)
+    except PsaGpuCancelled:
+        return None
+    Z, y = _unmirror(Z, y, n_mirror)
+    ps_tiny = 10 * math.sqrt(_FLOATMIN)  # compute.jl:236-238
+    Z = np.clip(Z, ps_tiny, np.inf)
+    err = 0
+    if re_calc:
+        levels, err = recalc_levels(Z, ax)
+    elif np.min(levels) > math.log10(np.max(Z)) or np.max(levels) < math.log10(np.min(Z)):
+        levels, err = recalc_levels(Z, ax)  # compute.jl:255-260
+    return Z, x, y, levels, err, Targ, np.array(eigA), algo

@@ -1,0 +1,651 @@
+// libpsagpu.so -- host side of the C ABI declared in include/psa_gpu.h.
+// One host thread drives every device of the context through per-device streams; all launches are
+// asynchronous and the only host<->device synchronisation is one tiny mapped-memory read per scheduler tick.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/psa_gpu.h"
+#include "psa_hess.cuh"
+#include "psa_square.cuh"
+
+namespace {
+
+using namespace psa;
+
+#define PSA_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      char buf_[512];                                                                          \
+      snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      ctx->err = buf_;                                                                         \
+      return e_ == cudaErrorMemoryAllocation ? PSA_ERR_NOMEM : PSA_ERR_CUDA;                   \
+    }                                                                                          \
+  } while (0)
+
+struct EventPair {
+  cudaEvent_t a, b;
+};
+
+struct Device {
+  int dev = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  // matrix
+  double2* T = nullptr;  // raw copy (m x n, ld = m)
+  double2* packA = nullptr;
+  double2* packB = nullptr;
+  // slots
+  int W = 0;
+  size_t vec_elems = 0;
+  double2 *Q0 = nullptr, *Q1 = nullptr, *Wv = nullptr;
+  int *slot_point = nullptr, *slot_iter = nullptr, *slot_sel = nullptr;
+  double2* slot_z = nullptr;
+  double *slot_beta = nullptr, *slot_sigold = nullptr, *hist_alpha = nullptr, *hist_beta = nullptr;
+  int *active = nullptr, *fresh = nullptr, *state = nullptr;
+  int* host_state = nullptr;      // pinned + mapped
+  int* host_state_dev = nullptr;  // device alias
+  unsigned long long* counts = nullptr;
+  // HessQR workspace
+  double2* R = nullptr;  // per-slot triangular factors
+  size_t R_elems = 0;
+  // grid buffers (owned unless device API)
+  double *x = nullptr, *y = nullptr, *Z = nullptr;
+  double2* q0 = nullptr;
+  int* iters = nullptr;
+  size_t x_cap = 0, y_cap = 0, q0_cap = 0, Z_cap = 0, it_cap = 0;
+  // events
+  std::vector<EventPair> ev;
+  cudaEvent_t g0 = nullptr, g1 = nullptr;
+};
+
+struct Context {
+  std::vector<Device> devs;
+  std::string err;
+  int m = 0, n = 0, n_pad = 0, nblk = 0, algo = PSA_ALGO_NONE;
+  double stats[PSA_NSTATS] = {0};
+  bool solve_attr_set = false;
+};
+
+template <typename T>
+int dev_alloc(Context* ctx, T** p, size_t count) {
+  if (*p) {
+    cudaFree(*p);
+    *p = nullptr;
+  }
+  PSA_CUDA(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
+  return PSA_OK;
+}
+
+void free_device(Device& d) {
+  cudaSetDevice(d.dev);
+  void* ptrs[] = {d.T, d.packA, d.packB, d.Q0, d.Q1, d.Wv, d.slot_point, d.slot_iter, d.slot_sel, d.slot_z,
+                  d.slot_beta, d.slot_sigold, d.hist_alpha, d.hist_beta, d.active, d.fresh, d.state, d.counts,
+                  d.R, d.x, d.y, d.Z, d.q0, d.iters};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (d.host_state) cudaFreeHost(d.host_state);
+  for (auto& e : d.ev) {
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  if (d.g0) cudaEventDestroy(d.g0);
+  if (d.g1) cudaEventDestroy(d.g1);
+  if (d.stream) cudaStreamDestroy(d.stream);
+  d = Device();
+}
+
+int ensure_slots(Context* ctx, Device& d, int want_W) {
+  const size_t vec_elems = (size_t)ctx->n_pad;
+  const bool hess = ctx->algo == PSA_ALGO_HESSQR;
+  const size_t r_elems = hess ? hess_R_elems(ctx->n) : 0;
+  if (d.W >= want_W && d.vec_elems == vec_elems && d.R_elems == r_elems) return PSA_OK;
+  PSA_CUDA(cudaSetDevice(d.dev));
+  const int W = want_W;
+  int rc;
+  if ((rc = dev_alloc(ctx, &d.Q0, (size_t)(W + 1) * vec_elems))) return rc;
+  if ((rc = dev_alloc(ctx, &d.Q1, (size_t)(W + 1) * vec_elems))) return rc;
+  if ((rc = dev_alloc(ctx, &d.Wv, (size_t)(W + 1) * vec_elems))) return rc;
+  if ((rc = dev_alloc(ctx, &d.slot_point, W + 1))) return rc;
+  if ((rc = dev_alloc(ctx, &d.slot_iter, W + 1))) return rc;
+  if ((rc = dev_alloc(ctx, &d.slot_sel, W + 1))) return rc;
+  if ((rc = dev_alloc(ctx, &d.slot_z, W + 1))) return rc;
+  if ((rc = dev_alloc(ctx, &d.slot_beta, W + 1))) return rc;
+  if ((rc = dev_alloc(ctx, &d.slot_sigold, W + 1))) return rc;
+  if ((rc = dev_alloc(ctx, &d.hist_alpha, (size_t)(W + 1) * HIST))) return rc;
+  if ((rc = dev_alloc(ctx, &d.hist_beta, (size_t)(W + 1) * HIST))) return rc;
+  if ((rc = dev_alloc(ctx, &d.active, W + 2 * NS))) return rc;
+  if ((rc = dev_alloc(ctx, &d.fresh, W + 1))) return rc;
+  if (hess && (rc = dev_alloc(ctx, &d.R, (size_t)(W + 1) * r_elems))) return rc;
+  // scratch slot W: benign, finite contents
+  PSA_CUDA(cudaMemsetAsync(d.Q0 + (size_t)W * vec_elems, 0, vec_elems * sizeof(double2), d.stream));
+  PSA_CUDA(cudaMemsetAsync(d.Q1 + (size_t)W * vec_elems, 0, vec_elems * sizeof(double2), d.stream));
+  PSA_CUDA(cudaMemsetAsync(d.Wv + (size_t)W * vec_elems, 0, vec_elems * sizeof(double2), d.stream));
+  PSA_CUDA(cudaMemsetAsync(d.slot_sel, 0, (W + 1) * sizeof(int), d.stream));
+  PSA_CUDA(cudaMemsetAsync(d.slot_z, 0, (W + 1) * sizeof(double2), d.stream));
+  if (hess) PSA_CUDA(cudaMemsetAsync(d.R + (size_t)W * r_elems, 0, r_elems * sizeof(double2), d.stream));
+  d.W = W;
+  d.vec_elems = vec_elems;
+  d.R_elems = r_elems;
+  return PSA_OK;
+}
+
+int slot_capacity(const Context* ctx, const Device& d, long long points) {
+  long long cap;
+  if (ctx->algo == PSA_ALGO_HESSQR) {
+    cap = hess_slot_capacity(ctx->n, d.num_sms);
+  } else {
+    cap = 2LL * d.num_sms * NS;  // two resident solve CTAs per SM, NS shifts each
+  }
+  long long w = std::min(cap, (points + NS - 1) / NS * NS);
+  return (int)std::max<long long>(w, NS);
+}
+
+EventPair& event_pair(Device& d, size_t i) {
+  while (d.ev.size() <= i) {
+    EventPair e;
+    cudaEventCreate(&e.a);
+    cudaEventCreate(&e.b);
+    d.ev.push_back(e);
+  }
+  return d.ev[i];
+}
+
+int set_solve_attr(Context* ctx) {
+  if (ctx->solve_attr_set) return PSA_OK;
+  for (auto& d : ctx->devs) {
+    PSA_CUDA(cudaSetDevice(d.dev));
+    PSA_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_SMEM));
+    PSA_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int rc = hess_set_attrs();
+    if (rc != 0) {
+      ctx->err = "cudaFuncSetAttribute failed for the HessQR kernels";
+      return PSA_ERR_CUDA;
+    }
+  }
+  ctx->solve_attr_set = true;
+  return PSA_OK;
+}
+
+SolveParams solve_params(const Context* ctx, const Device& d) {
+  SolveParams sp;
+  sp.packA = d.packA;
+  sp.packB = d.packB;
+  sp.n = ctx->n;
+  sp.n_pad = ctx->n_pad;
+  sp.nblk = ctx->nblk;
+  sp.active = d.active;
+  sp.n_active = d.state + 1;
+  sp.Q0 = d.Q0;
+  sp.Q1 = d.Q1;
+  sp.Wv = d.Wv;
+  sp.sel = d.slot_sel;
+  sp.z = d.slot_z;
+  return sp;
+}
+
+// pack / prepare the device-resident matrix on one device (d.T already holds the raw m x n copy)
+int prepare_matrix(Context* ctx, Device& d) {
+  PSA_CUDA(cudaSetDevice(d.dev));
+  if (ctx->algo == PSA_ALGO_SQ_LANC) {
+    const long long ntiles = tiles_per_phase(ctx->nblk);
+    int rc;
+    if ((rc = dev_alloc(ctx, &d.packA, (size_t)ntiles * TILE_ELEMS))) return rc;
+    if ((rc = dev_alloc(ctx, &d.packB, (size_t)ntiles * TILE_ELEMS))) return rc;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, d.stream);
+    const int grid = (int)std::min<long long>(2 * ntiles, 148LL * 32);
+    pack_kernel<<<grid, 256, 0, d.stream>>>(d.T, ctx->m, ctx->n, ctx->n_pad, ctx->nblk, d.packA, d.packB);
+    cudaEventRecord(e1, d.stream);
+    PSA_CUDA(cudaGetLastError());
+    PSA_CUDA(cudaStreamSynchronize(d.stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (&d == &ctx->devs[0]) ctx->stats[PSA_STAT_PACK_MS] = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    // the raw copy is no longer needed on the square path
+    cudaFree(d.T);
+    d.T = nullptr;
+  }
+  d.W = 0;  // slot buffers depend on n_pad / algo: force re-allocation
+  return PSA_OK;
+}
+
+int classify(int m, int n) {
+  if (m == n && n >= 55) return PSA_ALGO_SQ_LANC;        // compute.jl:478,534,565,594
+  if (m == n + 1 && m > 200 && n <= HQ_MAX_N) return PSA_ALGO_HESSQR;  // compute.jl:579 (bw == 2 is the caller's promise)
+  return PSA_ALGO_NONE;
+}
+
+struct GridArgs {
+  int lx, ly;
+  double tol;
+  int maxit;
+  double bigsigma;
+  volatile int* cancel;
+};
+
+// Run the tick loop on every device.  Per device: d.x, d.y, d.q0 are resident, d.Z / d.iters are the
+// (local point order) outputs.  Rows are dealt cyclically: device i owns rows i, i+ng, ...
+int run_grid(Context* ctx, const GridArgs& g, std::vector<double*>& Zout, std::vector<int*>& itout, int64_t* counts) {
+  const int ng = (int)ctx->devs.size();
+  int rc = set_solve_attr(ctx);
+  if (rc) return rc;
+  std::vector<int> rows(ng), P(ng), done(ng, 0);
+  std::vector<size_t> nev(ng, 0);
+  double launches = 0, solve_launches = 0, ticks = 0;
+  for (int i = 0; i < ng; ++i) {
+    Device& d = ctx->devs[i];
+    rows[i] = (g.ly - i + ng - 1) / ng;
+    P[i] = rows[i] * g.lx;
+    PSA_CUDA(cudaSetDevice(d.dev));
+    if ((rc = ensure_slots(ctx, d, slot_capacity(ctx, d, P[i])))) return rc;
+    PSA_CUDA(cudaMemsetAsync(d.slot_point, 0xff, (d.W + 1) * sizeof(int), d.stream));
+    PSA_CUDA(cudaMemsetAsync(d.state, 0, 4 * sizeof(int), d.stream));
+    PSA_CUDA(cudaMemsetAsync(d.counts, 0, PSA_NCOUNTS * sizeof(unsigned long long), d.stream));
+    PSA_CUDA(cudaEventRecord(d.g0, d.stream));
+    if (P[i] == 0) done[i] = 1;
+  }
+  const int hist_maxit = std::min(g.maxit, HIST - 2);
+  int remaining = 0;
+  for (int i = 0; i < ng; ++i) remaining += !done[i];
+  bool cancelled = false;
+  while (remaining > 0) {
+    if (g.cancel && *g.cancel == 1) {
+      cancelled = true;
+      break;
+    }
+    // 1. schedule
+    for (int i = 0; i < ng; ++i) {
+      if (done[i]) continue;
+      Device& d = ctx->devs[i];
+      PSA_CUDA(cudaSetDevice(d.dev));
+      SchedParams sp;
+      sp.W = d.W;
+      sp.P = P[i];
+      sp.rows_local = rows[i];
+      sp.row0 = i;
+      sp.row_step = ng;
+      sp.x = d.x;
+      sp.y = d.y;
+      sp.slot_point = d.slot_point;
+      sp.slot_z = d.slot_z;
+      sp.slot_iter = d.slot_iter;
+      sp.slot_beta = d.slot_beta;
+      sp.slot_sigold = d.slot_sigold;
+      sp.slot_sel = d.slot_sel;
+      sp.active = d.active;
+      sp.fresh = d.fresh;
+      sp.state = d.state;
+      sp.host_state = d.host_state_dev;
+      sched_kernel<<<1, 1024, 0, d.stream>>>(sp);
+      launches += 1;
+    }
+    // 2. read back the tick's counts and launch the tick
+    for (int i = 0; i < ng; ++i) {
+      if (done[i]) continue;
+      Device& d = ctx->devs[i];
+      PSA_CUDA(cudaSetDevice(d.dev));
+      PSA_CUDA(cudaStreamSynchronize(d.stream));
+      const int n_active = d.host_state[1], n_fresh = d.host_state[2];
+      if (n_active == 0) {
+        done[i] = 1;
+        --remaining;
+        continue;
+      }
+      ticks += (i == 0);
+      EventPair& ep = event_pair(d, nev[i]++);
+      if (ctx->algo == PSA_ALGO_SQ_LANC) {
+        if (n_fresh > 0) {
+          init_fresh_kernel<<<n_fresh, 256, 0, d.stream>>>(d.fresh, ctx->n_pad, ctx->n, d.q0, d.Q0);
+          launches += 1;
+        }
+        const int panels = (n_active + NS - 1) / NS;
+        PSA_CUDA(cudaEventRecord(ep.a, d.stream));
+        solve_kernel<<<panels, SOLVE_THREADS, SOLVE_SMEM, d.stream>>>(solve_params(ctx, d));
+        PSA_CUDA(cudaEventRecord(ep.b, d.stream));
+        launches += 1;
+        solve_launches += (i == 0);
+      } else {
+        HessTick ht;
+        ht.m = ctx->m;
+        ht.n = ctx->n;
+        ht.n_pad = ctx->n_pad;
+        ht.H = d.T;
+        ht.R = d.R;
+        ht.q0 = d.q0;
+        ht.fresh = d.fresh;
+        ht.n_fresh = n_fresh;
+        ht.active = d.active;
+        ht.n_active = n_active;
+        ht.n_active_dev = d.state + 1;
+        ht.Q0 = d.Q0;
+        ht.Q1 = d.Q1;
+        ht.Wv = d.Wv;
+        ht.sel = d.slot_sel;
+        ht.z = d.slot_z;
+        PSA_CUDA(cudaEventRecord(ep.a, d.stream));
+        const int nl = hess_launch_tick(ht, d.stream, ep.a, ep.b);
+        launches += nl;
+        solve_launches += (i == 0);
+      }
+      LanczosParams lp;
+      lp.n = ctx->n;
+      lp.n_pad = ctx->n_pad;
+      lp.W = d.W;
+      lp.active = d.active;
+      lp.n_active = d.state + 1;
+      lp.Q0 = d.Q0;
+      lp.Q1 = d.Q1;
+      lp.Wv = d.Wv;
+      lp.slot_point = d.slot_point;
+      lp.slot_iter = d.slot_iter;
+      lp.slot_beta = d.slot_beta;
+      lp.slot_sigold = d.slot_sigold;
+      lp.slot_sel = d.slot_sel;
+      lp.hist_alpha = d.hist_alpha;
+      lp.hist_beta = d.hist_beta;
+      lp.tol = g.tol;
+      lp.maxit = hist_maxit;
+      lp.bigsigma = g.bigsigma;
+      lp.Z = Zout[i];
+      lp.iters = itout[i];
+      lp.counts = d.counts;
+      lanczos_kernel<<<n_active, LZ_THREADS, 0, d.stream>>>(lp);
+      launches += 1;
+      PSA_CUDA(cudaGetLastError());
+    }
+  }
+  // drain, collect counts + timing
+  unsigned long long tot[PSA_NCOUNTS] = {0, 0, 0, 0};
+  for (int i = 0; i < ng; ++i) {
+    Device& d = ctx->devs[i];
+    PSA_CUDA(cudaSetDevice(d.dev));
+    PSA_CUDA(cudaEventRecord(d.g1, d.stream));
+    PSA_CUDA(cudaStreamSynchronize(d.stream));
+    unsigned long long c[PSA_NCOUNTS];
+    PSA_CUDA(cudaMemcpy(c, d.counts, sizeof c, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < PSA_NCOUNTS; ++k) tot[k] += c[k];
+    if (i == 0) {
+      double solve_ms = 0;
+      for (size_t e = 0; e < nev[i]; ++e) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, d.ev[e].a, d.ev[e].b);
+        solve_ms += ms;
+      }
+      float gms = 0;
+      cudaEventElapsedTime(&gms, d.g0, d.g1);
+      ctx->stats[PSA_STAT_SOLVE_MS] = solve_ms;
+      ctx->stats[PSA_STAT_GRID_MS] = gms;
+    }
+  }
+  ctx->stats[PSA_STAT_SOLVE_LAUNCHES] = solve_launches;
+  ctx->stats[PSA_STAT_TOTAL_LAUNCHES] = launches;
+  ctx->stats[PSA_STAT_TICKS] = ticks;
+  const double nn = (double)ctx->n;
+  if (ctx->algo == PSA_ALGO_SQ_LANC) {
+    ctx->stats[PSA_STAT_FLOPS] = 8.0 * nn * nn * (double)tot[PSA_COUNT_TOTAL_ITERS];
+    ctx->stats[PSA_STAT_BYTES] = 0.0;
+  } else {
+    ctx->stats[PSA_STAT_FLOPS] = 10.0 * nn * nn * (double)tot[PSA_COUNT_POINTS] + 8.0 * nn * nn * (double)tot[PSA_COUNT_TOTAL_ITERS];
+    ctx->stats[PSA_STAT_BYTES] = 16.0 * ctx->m * nn * (double)tot[PSA_COUNT_POINTS] + 16.0 * nn * nn * (double)tot[PSA_COUNT_TOTAL_ITERS];
+  }
+  if (counts)
+    for (int k = 0; k < PSA_NCOUNTS; ++k) counts[k] = (int64_t)tot[k];
+  return cancelled ? PSA_ERR_CANCELLED : PSA_OK;
+}
+
+template <typename T>
+int ensure_cap(Context* ctx, T** p, size_t* cap, size_t want) {
+  if (*cap >= want && *p) return PSA_OK;
+  int rc = dev_alloc(ctx, p, want);
+  if (rc) return rc;
+  *cap = want;
+  return PSA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* psa_gpu_version(void) { return "psagpu 0.1.0 sm_100a"; }
+
+const char* psa_gpu_strerror(int status) {
+  switch (status) {
+    case PSA_OK: return "ok";
+    case PSA_ERR_ARG: return "invalid argument";
+    case PSA_ERR_CUDA: return "CUDA error";
+    case PSA_ERR_CANCELLED: return "computation cancelled";
+    case PSA_ERR_UNSUPPORTED: return "matrix shape not covered by the GPU path (use the host algorithm)";
+    case PSA_ERR_NODEVICE: return "no usable sm_100 CUDA device";
+    case PSA_ERR_NOMATRIX: return "no matrix set";
+    case PSA_ERR_NCCL: return "NCCL error";
+    case PSA_ERR_NOMEM: return "device memory allocation failed";
+    default: return "unknown status";
+  }
+}
+
+const char* psa_gpu_last_error(void* vctx) {
+  if (!vctx) return "";
+  return static_cast<Context*>(vctx)->err.c_str();
+}
+
+int psa_gpu_init(int ngpus, const int* device_ids, void** out) {
+  if (!out || ngpus < 1) return PSA_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) return PSA_ERR_NODEVICE;
+  if (ngpus > count) return PSA_ERR_NODEVICE;
+  Context* ctx = new Context();
+  ctx->devs.resize(ngpus);
+  for (int i = 0; i < ngpus; ++i) {
+    Device& d = ctx->devs[i];
+    d.dev = device_ids ? device_ids[i] : i;
+    cudaDeviceProp prop;
+    if (d.dev < 0 || d.dev >= count || cudaGetDeviceProperties(&prop, d.dev) != cudaSuccess || prop.major != 10) {
+      for (auto& dd : ctx->devs) free_device(dd);
+      delete ctx;
+      return PSA_ERR_NODEVICE;
+    }
+    d.num_sms = prop.multiProcessorCount;
+    bool ok = cudaSetDevice(d.dev) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&d.state, 4 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&d.counts, PSA_NCOUNTS * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaHostAlloc((void**)&d.host_state, 4 * sizeof(int), cudaHostAllocMapped) == cudaSuccess;
+    ok = ok && cudaHostGetDevicePointer((void**)&d.host_state_dev, d.host_state, 0) == cudaSuccess;
+    ok = ok && cudaEventCreate(&d.g0) == cudaSuccess && cudaEventCreate(&d.g1) == cudaSuccess;
+    if (!ok) {
+      for (auto& dd : ctx->devs) free_device(dd);
+      delete ctx;
+      return PSA_ERR_CUDA;
+    }
+  }
+  *out = ctx;
+  return PSA_OK;
+}
+
+int psa_gpu_free(void* vctx) {
+  if (!vctx) return PSA_ERR_ARG;
+  Context* ctx = static_cast<Context*>(vctx);
+  for (auto& d : ctx->devs) free_device(d);
+  delete ctx;
+  return PSA_OK;
+}
+
+static int set_matrix_common(Context* ctx, const double* T, int64_t ldt, int m, int n, bool on_device) {
+  if (!T || m < n || n < 1 || ldt < m) return PSA_ERR_ARG;
+  const int algo = classify(m, n);
+  if (algo == PSA_ALGO_NONE) return PSA_ERR_UNSUPPORTED;
+  ctx->algo = PSA_ALGO_NONE;
+  ctx->m = m;
+  ctx->n = n;
+  ctx->n_pad = (n + MB - 1) / MB * MB;
+  ctx->nblk = ctx->n_pad / MB;
+  // raw copy to device 0, then replicate
+  Device& d0 = ctx->devs[0];
+  PSA_CUDA(cudaSetDevice(d0.dev));
+  int rc;
+  if ((rc = dev_alloc(ctx, &d0.T, (size_t)m * n))) return rc;
+  PSA_CUDA(cudaMemcpy2DAsync(d0.T, (size_t)m * 16, T, (size_t)ldt * 16, (size_t)m * 16, n,
+                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, d0.stream));
+  PSA_CUDA(cudaStreamSynchronize(d0.stream));
+  for (size_t i = 1; i < ctx->devs.size(); ++i) {
+    Device& d = ctx->devs[i];
+    PSA_CUDA(cudaSetDevice(d.dev));
+    if ((rc = dev_alloc(ctx, &d.T, (size_t)m * n))) return rc;
+    PSA_CUDA(cudaMemcpyPeerAsync(d.T, d.dev, d0.T, d0.dev, (size_t)m * n * 16, d.stream));
+  }
+  ctx->algo = algo;
+  for (auto& d : ctx->devs)
+    if ((rc = prepare_matrix(ctx, d))) {
+      ctx->algo = PSA_ALGO_NONE;
+      return rc;
+    }
+  return PSA_OK;
+}
+
+int psa_gpu_set_matrix(void* vctx, const double* T, int64_t ldt, int m, int n) {
+  if (!vctx) return PSA_ERR_ARG;
+  return set_matrix_common(static_cast<Context*>(vctx), T, ldt, m, n, false);
+}
+
+int psa_gpu_set_matrix_device(void* vctx, const double* d_T, int64_t ldt, int m, int n) {
+  if (!vctx) return PSA_ERR_ARG;
+  return set_matrix_common(static_cast<Context*>(vctx), d_T, ldt, m, n, true);
+}
+
+int psa_gpu_grid(void* vctx, const double* x, int lx, const double* y, int ly, const double* q0, double tol, int maxit,
+                 double bigsigma, double* Z, int32_t* iters, int64_t* counts, int* algo, volatile int* cancel) {
+  if (!vctx) return PSA_ERR_ARG;
+  Context* ctx = static_cast<Context*>(vctx);
+  if (ctx->algo == PSA_ALGO_NONE) return PSA_ERR_NOMATRIX;
+  if (!x || !y || !q0 || !Z || lx < 1 || ly < 1 || maxit < 1) return PSA_ERR_ARG;
+  if (algo) *algo = ctx->algo;
+  const int ng = (int)ctx->devs.size();
+  std::vector<double*> Zout(ng);
+  std::vector<int*> itout(ng);
+  int rc;
+  for (int i = 0; i < ng; ++i) {
+    Device& d = ctx->devs[i];
+    PSA_CUDA(cudaSetDevice(d.dev));
+    const int rows = (ly - i + ng - 1) / ng;
+    const size_t P = (size_t)rows * lx;
+    if ((rc = ensure_cap(ctx, &d.x, &d.x_cap, (size_t)lx))) return rc;
+    if ((rc = ensure_cap(ctx, &d.y, &d.y_cap, (size_t)ly))) return rc;
+    if ((rc = ensure_cap(ctx, &d.q0, &d.q0_cap, (size_t)ctx->n))) return rc;
+    if ((rc = ensure_cap(ctx, &d.Z, &d.Z_cap, P))) return rc;
+    if ((rc = ensure_cap(ctx, &d.iters, &d.it_cap, P))) return rc;
+    PSA_CUDA(cudaMemcpyAsync(d.x, x, lx * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+    PSA_CUDA(cudaMemcpyAsync(d.y, y, ly * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+    PSA_CUDA(cudaMemcpyAsync(d.q0, q0, (size_t)ctx->n * 16, cudaMemcpyHostToDevice, d.stream));
+    Zout[i] = d.Z;
+    itout[i] = d.iters;
+  }
+  GridArgs g{lx, ly, tol, maxit, bigsigma, cancel};
+  rc = run_grid(ctx, g, Zout, itout, counts);
+  if (rc != PSA_OK) return rc;
+  // gather: device i owns rows i, i+ng, ... ; local layout is rows_i x lx column-major
+  std::vector<double> zb;
+  std::vector<int> ib;
+  for (int i = 0; i < ng; ++i) {
+    Device& d = ctx->devs[i];
+    PSA_CUDA(cudaSetDevice(d.dev));
+    const int rows = (ly - i + ng - 1) / ng;
+    const size_t P = (size_t)rows * lx;
+    if (P == 0) continue;
+    if (ng == 1) {
+      PSA_CUDA(cudaMemcpy(Z, d.Z, P * sizeof(double), cudaMemcpyDeviceToHost));
+      if (iters) PSA_CUDA(cudaMemcpy(iters, d.iters, P * sizeof(int), cudaMemcpyDeviceToHost));
+    } else {
+      zb.resize(P);
+      PSA_CUDA(cudaMemcpy(zb.data(), d.Z, P * sizeof(double), cudaMemcpyDeviceToHost));
+      for (int k = 0; k < lx; ++k)
+        for (int jr = 0; jr < rows; ++jr) Z[(size_t)k * ly + i + (size_t)jr * ng] = zb[(size_t)k * rows + jr];
+      if (iters) {
+        ib.resize(P);
+        PSA_CUDA(cudaMemcpy(ib.data(), d.iters, P * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < lx; ++k)
+          for (int jr = 0; jr < rows; ++jr) iters[(size_t)k * ly + i + (size_t)jr * ng] = ib[(size_t)k * rows + jr];
+      }
+    }
+  }
+  return PSA_OK;
+}
+
+int psa_gpu_grid_device(void* vctx, const double* d_x, int lx, const double* d_y, int ly, const double* d_q0, double tol,
+                        int maxit, double bigsigma, double* d_Z, int32_t* d_iters, int64_t* counts, int* algo,
+                        volatile int* cancel) {
+  if (!vctx) return PSA_ERR_ARG;
+  Context* ctx = static_cast<Context*>(vctx);
+  if (ctx->algo == PSA_ALGO_NONE) return PSA_ERR_NOMATRIX;
+  if (ctx->devs.size() != 1) return PSA_ERR_UNSUPPORTED;
+  if (!d_x || !d_y || !d_q0 || !d_Z || lx < 1 || ly < 1 || maxit < 1) return PSA_ERR_ARG;
+  if (algo) *algo = ctx->algo;
+  Device& d = ctx->devs[0];
+  PSA_CUDA(cudaSetDevice(d.dev));
+  // borrow the caller's buffers for this call
+  double *sx = d.x, *sy = d.y;
+  double2* sq = d.q0;
+  d.x = const_cast<double*>(d_x);
+  d.y = const_cast<double*>(d_y);
+  d.q0 = reinterpret_cast<double2*>(const_cast<double*>(d_q0));
+  std::vector<double*> Zout{d_Z};
+  std::vector<int*> itout{d_iters};
+  GridArgs g{lx, ly, tol, maxit, bigsigma, cancel};
+  int rc = run_grid(ctx, g, Zout, itout, counts);
+  d.x = sx;
+  d.y = sy;
+  d.q0 = sq;
+  return rc;
+}
+
+int psa_gpu_apply_resolvent(void* vctx, const double* z, int ns, const double* Q, double* V) {
+  if (!vctx) return PSA_ERR_ARG;
+  Context* ctx = static_cast<Context*>(vctx);
+  if (ctx->algo != PSA_ALGO_SQ_LANC) return ctx->algo == PSA_ALGO_NONE ? PSA_ERR_NOMATRIX : PSA_ERR_UNSUPPORTED;
+  if (!z || !Q || !V || ns < 1) return PSA_ERR_ARG;
+  Device& d = ctx->devs[0];
+  PSA_CUDA(cudaSetDevice(d.dev));
+  int rc = set_solve_attr(ctx);
+  if (rc) return rc;
+  const int W = (ns + NS - 1) / NS * NS;
+  if ((rc = ensure_slots(ctx, d, std::max(W, d.W)))) return rc;
+  double2 *dQ = nullptr, *dz = nullptr, *dV = nullptr;
+  const size_t n = ctx->n;
+  if ((rc = dev_alloc(ctx, &dQ, ns * n))) return rc;
+  if ((rc = dev_alloc(ctx, &dz, (size_t)ns))) return rc;
+  if ((rc = dev_alloc(ctx, &dV, ns * n))) return rc;
+  PSA_CUDA(cudaMemcpyAsync(dQ, Q, ns * n * 16, cudaMemcpyHostToDevice, d.stream));
+  PSA_CUDA(cudaMemcpyAsync(dz, z, (size_t)ns * 16, cudaMemcpyHostToDevice, d.stream));
+  load_slots_kernel<<<W, 256, 0, d.stream>>>(ns, ctx->n, ctx->n_pad, dQ, dz, d.Q0, d.slot_z, d.slot_sel, d.active, d.W,
+                                             d.state);
+  solve_kernel<<<W / NS, SOLVE_THREADS, SOLVE_SMEM, d.stream>>>(solve_params(ctx, d));
+  store_slots_kernel<<<ns, 256, 0, d.stream>>>(ctx->n, ctx->n_pad, d.Wv, dV);
+  PSA_CUDA(cudaGetLastError());
+  PSA_CUDA(cudaMemcpyAsync(V, dV, ns * n * 16, cudaMemcpyDeviceToHost, d.stream));
+  PSA_CUDA(cudaStreamSynchronize(d.stream));
+  cudaFree(dQ);
+  cudaFree(dz);
+  cudaFree(dV);
+  return PSA_OK;
+}
+
+int psa_gpu_last_stats(void* vctx, double* stats) {
+  if (!vctx || !stats) return PSA_ERR_ARG;
+  Context* ctx = static_cast<Context*>(vctx);
+  for (int i = 0; i < PSA_NSTATS; ++i) stats[i] = ctx->stats[i];
+  return PSA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,256 @@
+// Rectangular-Hessenberg (:HessQR) path kernels.
+//
+// Reference: /root/reference/src/compute.jl:571-592 -- per grid point, shift the diagonal of the (n+1) x n
+// Hessenberg matrix (573), sweep n-1 Givens rotations over row pairs (581-587), keep triu(T1[1:n,1:n]) (592),
+// then run the inverse-Lanczos recurrence on that private triangular factor (602).  Every shift owns its own
+// R, so this path is BLAS-2 and bound by memory bandwidth (HBM / L2), not by the tensor pipe.
+#pragma once
+#include "psa_common.cuh"
+
+namespace psa {
+
+constexpr int HQ_MAX_N = 1024;   // one thread per column in the QR sweep
+constexpr int HS_THREADS = 256;  // solve kernel
+constexpr int HB = 32;           // diagonal block of the per-shift triangular solves
+
+inline size_t hess_R_elems(int n) { return (size_t)n * n; }  // column-major n x n per slot, ld = n
+inline long long hess_slot_capacity(int n, int num_sms) {
+  (void)n;
+  return 4LL * num_sms;
+}
+
+// zlartg-convention Givens (Julia `givens(f,g,1,2)`, compute.jl:585): [c s; -conj(s) c][f; g] = [r; 0], c real
+__device__ __forceinline__ void givens_cs(double2 f, double2 g, double& c, double2& s) {
+  if (g.x == 0.0 && g.y == 0.0) {
+    c = 1.0;
+    s = make_double2(0.0, 0.0);
+    return;
+  }
+  const double ag = hypot(g.x, g.y);
+  if (f.x == 0.0 && f.y == 0.0) {
+    c = 0.0;
+    s = make_double2(g.x / ag, -g.y / ag);
+    return;
+  }
+  const double af = hypot(f.x, f.y);
+  const double d = hypot(af, ag);
+  c = af / d;
+  const double2 ph = make_double2(f.x / af, f.y / af);
+  const double2 cg = make_double2(g.x / d, -g.y / d);
+  s = cmul(ph, cg);
+}
+
+// One CTA per freshly scheduled slot, one thread per column c.  The thread keeps the running entry of row
+// jj ("carry") in a register: rotation jj turns (carry, T1[jj+1,c]) into the final R[jj,c] and the next carry.
+// Column jj's owner produces the rotation; it is broadcast through (double-buffered) shared memory.
+__global__ void hess_qr_kernel(const int* __restrict__ fresh, int m, int n, const double2* __restrict__ H,
+                               const double2* __restrict__ zs, double2* __restrict__ Rall,
+                               const double2* __restrict__ q0, int n_pad, double2* __restrict__ Q0) {
+  __shared__ double g_c[2];
+  __shared__ double2 g_s[2];
+  const int slot = fresh[blockIdx.x];
+  const int c = threadIdx.x;
+  const double2 z = zs[slot];
+  double2* R = Rall + (size_t)slot * n * n;
+  // q <- q0 for this slot
+  double2* q = Q0 + (size_t)slot * n_pad;
+  for (int i = c; i < n_pad; i += blockDim.x) q[i] = (i < n) ? q0[i] : make_double2(0.0, 0.0);
+
+  const bool live = c < n;
+  const double2* Hc = H + (size_t)(live ? c : 0) * m;
+  double2 carry = make_double2(0.0, 0.0);
+  if (live) {
+    carry = Hc[0];
+    if (c == 0) {
+      carry.x -= z.x;
+      carry.y -= z.y;
+    }
+  }
+  for (int jj = 0; jj < n - 1; ++jj) {
+    double2 b = make_double2(0.0, 0.0);
+    if (live && c >= jj) {
+      b = Hc[jj + 1];
+      if (jj + 1 == c) {
+        b.x -= z.x;
+        b.y -= z.y;
+      }
+    }
+    if (c == jj) {
+      double cs;
+      double2 sn;
+      givens_cs(carry, b, cs, sn);
+      g_c[jj & 1] = cs;
+      g_s[jj & 1] = sn;
+    }
+    __syncthreads();
+    if (live && c >= jj) {
+      const double cs = g_c[jj & 1];
+      const double2 sn = g_s[jj & 1];
+      const double2 a = carry;
+      // R[jj,c] = cs*a + sn*b ; carry = -conj(sn)*a + cs*b
+      double2 r = cmul(sn, b);
+      r.x = fma(cs, a.x, r.x);
+      r.y = fma(cs, a.y, r.y);
+      R[(size_t)c * n + jj] = r;
+      const double2 sc = make_double2(-sn.x, sn.y);  // -conj(sn)
+      double2 nc = cmul(sc, a);
+      nc.x = fma(cs, b.x, nc.x);
+      nc.y = fma(cs, b.y, nc.y);
+      carry = nc;
+    }
+  }
+  if (c == n - 1) R[(size_t)c * n + (n - 1)] = carry;  // H[n+1,n] is never rotated in (reference quirk)
+}
+
+// One CTA per active slot: w = R^{-H} q (forward, dot form) then v = R^{-1} w (backward, axpy form); v -> Wv.
+struct HessSolveParams {
+  int n, n_pad;
+  const int* active;
+  const int* n_active;
+  const double2* R;
+  const double2* Q0;
+  const double2* Q1;
+  double2* Wv;
+  const int* sel;
+};
+
+__global__ void __launch_bounds__(HS_THREADS) hess_solve_kernel(HessSolveParams P) {
+  extern __shared__ __align__(16) unsigned char hsm[];
+  double2* w = reinterpret_cast<double2*>(hsm);                       // n_pad
+  double2* tri = w + P.n_pad;                                         // HB x (HB+1), tri[col*(HB+1) + row]
+  double2* part = tri + HB * (HB + 1);                                // HB
+  if ((int)blockIdx.x >= *P.n_active) return;
+  const int slot = P.active[blockIdx.x];
+  const int n = P.n, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const double2* R = P.R + (size_t)slot * n * n;
+  const double2* q = (P.sel[slot] ? P.Q1 : P.Q0) + (size_t)slot * P.n_pad;
+  const int nb = (n + HB - 1) / HB;
+
+  // ---- forward: (R^H) w = q ----
+  for (int J = 0; J < nb; ++J) {
+    const int j0 = J * HB, jw = min(HB, n - j0);
+    // diagonal block -> smem (coalesced down each column)
+    for (int e = tid; e < HB * HB; e += HS_THREADS) {
+      const int col = e >> 5, row = e & 31;
+      tri[col * (HB + 1) + row] = (col < jw && row <= col) ? R[(size_t)(j0 + col) * n + j0 + row] : make_double2(0.0, 0.0);
+    }
+    // partial dots against the already known w[0:j0]
+    for (int jj = warp; jj < jw; jj += HS_THREADS / 32) {
+      const double2* col = R + (size_t)(j0 + jj) * n;
+      double sr = 0.0, si = 0.0;
+      for (int i = lane; i < j0; i += 32) {
+        const double2 r = col[i], x = w[i];
+        sr = fma(r.x, x.x, sr);
+        sr = fma(r.y, x.y, sr);   // conj(r)*x
+        si = fma(r.x, x.y, si);
+        si = fma(-r.y, x.x, si);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sr += __shfl_xor_sync(0xffffffffu, sr, o);
+        si += __shfl_xor_sync(0xffffffffu, si, o);
+      }
+      if (lane == 0) part[jj] = make_double2(sr, si);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double2 val = make_double2(0.0, 0.0);
+      if (lane < jw) {
+        const double2 qq = q[j0 + lane], pp = part[lane];
+        val = make_double2(qq.x - pp.x, qq.y - pp.y);
+      }
+      for (int i = 0; i < jw; ++i) {
+        if (lane == i) {
+          double2 d = tri[i * (HB + 1) + i];
+          d.y = -d.y;
+          val = cmul(val, crecip(d));
+        }
+        const double wx = __shfl_sync(0xffffffffu, val.x, i), wy = __shfl_sync(0xffffffffu, val.y, i);
+        if (lane > i && lane < jw) {
+          double2 r = tri[lane * (HB + 1) + i];
+          r.y = -r.y;
+          cmsub(val, r, make_double2(wx, wy));
+        }
+      }
+      if (lane < jw) w[j0 + lane] = val;
+    }
+    __syncthreads();
+  }
+  // ---- backward: R v = w (in place in smem) ----
+  for (int J = nb - 1; J >= 0; --J) {
+    const int j0 = J * HB, jw = min(HB, n - j0);
+    for (int e = tid; e < HB * HB; e += HS_THREADS) {
+      const int col = e >> 5, row = e & 31;
+      tri[col * (HB + 1) + row] = (col < jw && row <= col) ? R[(size_t)(j0 + col) * n + j0 + row] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double2 val = lane < jw ? w[j0 + lane] : make_double2(0.0, 0.0);
+      for (int k = jw - 1; k >= 0; --k) {
+        if (lane == k) val = cmul(val, crecip(tri[k * (HB + 1) + k]));
+        const double vx = __shfl_sync(0xffffffffu, val.x, k), vy = __shfl_sync(0xffffffffu, val.y, k);
+        if (lane < k) cmsub(val, tri[k * (HB + 1) + lane], make_double2(vx, vy));
+      }
+      if (lane < jw) w[j0 + lane] = val;
+    }
+    __syncthreads();
+    // rows above the block: w[i] -= sum_k R[i, j0+k] v[j0+k]
+    for (int i = tid; i < j0; i += HS_THREADS) {
+      double2 acc = w[i];
+      for (int k = 0; k < jw; ++k) cmsub(acc, R[(size_t)(j0 + k) * n + i], w[j0 + k]);
+      w[i] = acc;
+    }
+    __syncthreads();
+  }
+  double2* out = P.Wv + (size_t)slot * P.n_pad;
+  for (int i = tid; i < n; i += HS_THREADS) out[i] = w[i];
+}
+
+struct HessTick {
+  int m, n, n_pad;
+  const double2* H;
+  double2* R;
+  const double2* q0;
+  const int* fresh;
+  int n_fresh;
+  const int* active;
+  int n_active;
+  const int* n_active_dev;
+  double2 *Q0, *Q1, *Wv;
+  const int* sel;
+  const double2* z;
+};
+
+inline size_t hess_solve_smem(int n_pad) { return ((size_t)n_pad + HB * (HB + 1) + HB) * sizeof(double2); }
+
+inline int hess_set_attrs() {
+  cudaError_t e = cudaFuncSetAttribute(hess_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  return e == cudaSuccess ? 0 : -1;
+}
+
+// launches the tick's HessQR kernels; ev_a was recorded by the caller, ev_b is recorded here. Returns #launches.
+inline int hess_launch_tick(const HessTick& t, cudaStream_t stream, cudaEvent_t ev_a, cudaEvent_t ev_b) {
+  (void)ev_a;
+  int launches = 0;
+  if (t.n_fresh > 0) {
+    const int threads = (t.n + 31) / 32 * 32;
+    hess_qr_kernel<<<t.n_fresh, threads, 0, stream>>>(t.fresh, t.m, t.n, t.H, t.z, t.R, t.q0, t.n_pad, t.Q0);
+    ++launches;
+  }
+  HessSolveParams sp;
+  sp.n = t.n;
+  sp.n_pad = t.n_pad;
+  sp.active = t.active;
+  sp.n_active = t.n_active_dev;
+  sp.R = t.R;
+  sp.Q0 = t.Q0;
+  sp.Q1 = t.Q1;
+  sp.Wv = t.Wv;
+  sp.sel = t.sel;
+  hess_solve_kernel<<<t.n_active, HS_THREADS, hess_solve_smem(t.n_pad), stream>>>(sp);
+  ++launches;
+  cudaEventRecord(ev_b, stream);
+  return launches;
+}
+
+}  // namespace psa

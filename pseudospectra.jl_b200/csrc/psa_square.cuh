@@ -1,0 +1,612 @@
+// Square (:sq_lanc) path kernels: multi-shift blocked triangular solves on FP64 tensor cores.
+//
+// Replaces, for hundreds of shifts at once, the two BLAS ztrsv calls per Lanczos iteration at
+// /root/reference/src/compute.jl:630  (`v = F1 \ (F1' \ q)`), where F1 = T - z I differs between grid points
+// only on its diagonal (compute.jl:405,595).  T is shared by all shifts, so the off-diagonal block updates
+// are a dense contraction (complex GEMM as 4 real DMMA per 8x8x4 block); only the 16x16 diagonal blocks are
+// per-shift.  See DESIGN.md for the layout and the step schedule.
+#pragma once
+#include "psa_common.cuh"
+
+namespace psa {
+
+// ---- tiling constants -------------------------------------------------------------------------------
+constexpr int MB = 64;                        // rows per block row (M tile)
+constexpr int KC = 16;                        // contraction chunk (one pipeline step)
+constexpr int NS = 64;                        // shifts per panel (N tile) = one CTA
+constexpr int CPB = MB / KC;                  // chunks per block = 4
+constexpr int TILE_ELEMS = MB * KC;           // complex elements per packed T tile
+constexpr int TILE_BYTES = TILE_ELEMS * 16;   // 16 KiB
+constexpr int XROW_BYTES = KC * 16 + 64;      // 320: X smem row stride (64 B pad -> conflict-free B-fragment loads)
+constexpr int XT_BYTES = NS * XROW_BYTES;     // 20 KiB
+constexpr int STAGE_BYTES = TILE_BYTES + XT_BYTES;
+constexpr int STAGES = 3;                     // <= 4 (producer/consumer distance rule)
+constexpr int SOLVE_THREADS = 256;
+constexpr int SOLVE_SMEM_AUX = 32 + NS * 16 + NS * 8 * 2;  // mbarriers (padded) + shifts + 2 pointer tables
+constexpr int SOLVE_SMEM = STAGES * STAGE_BYTES + SOLVE_SMEM_AUX;
+static_assert(STAGES * 8 <= 32, "mbarrier block");
+constexpr int HIST = 128;                     // per-slot alpha/beta history stride (maxit <= 126)
+
+__host__ __device__ inline long long tiles_per_phase(int nblk) { return 2LL * nblk * (nblk + 1); }
+// tile (I, c), c in [0, 4I+4): offset in tiles within one phase stream
+__host__ __device__ inline long long tile_index(int I, int c) { return 2LL * I * (I + 1) + c; }
+
+// ---- one-time packing of T into DMMA A-fragment order -----------------------------------------------
+// Processing index p in [0, n_pad).  Phase A (adjoint, L_A = T^H, forward order): orig(p) = p.
+// Phase B (T upper, processed bottom-up): orig(p) = n_pad-1-p.  Both become "lower triangular, forward".
+//   L_A[p][p'] = conj(T[orig(p')][orig(p)]),   L_B[p][p'] = T[orig(p)][orig(p')],   p' <= p, else 0.
+// Padding (orig >= n): identity.  Tile (I,c) holds rows 64I.., columns 16c.. as fragments:
+//   element (m, kk) -> double2 index ((kk>>2)*8 + (m>>3))*32 + (m&7)*4 + (kk&3).
+__global__ void pack_kernel(const double2* __restrict__ T, long long ldt, int n, int n_pad, int nblk,
+                            double2* __restrict__ packA, double2* __restrict__ packB) {
+  const long long ntiles = tiles_per_phase(nblk);
+  for (long long tile = blockIdx.x; tile < 2 * ntiles; tile += gridDim.x) {
+    const int phase = tile >= ntiles;
+    const long long t = phase ? tile - ntiles : tile;
+    // invert tile_index: I = largest with 2I(I+1) <= t
+    int I = (int)((sqrt(1.0 + 2.0 * (double)t) - 1.0) * 0.5);
+    while (tile_index(I + 1, 0) <= t) ++I;
+    while (tile_index(I, 0) > t) --I;
+    const int c = (int)(t - tile_index(I, 0));
+    double2* out = (phase ? packB : packA) + t * TILE_ELEMS;
+    for (int e = threadIdx.x; e < TILE_ELEMS; e += blockDim.x) {
+      int m, kk;
+      if (phase == 0) {  // reads run down a column of T: kk fastest
+        kk = e & 15;
+        m = e >> 4;
+      } else {  // reads run down a column of T: m fastest (orig row = n_pad-1-p)
+        m = e & 63;
+        kk = e >> 6;
+      }
+      const int p = MB * I + m, pp = KC * c + kk;
+      double2 v = make_double2(0.0, 0.0);
+      if (pp <= p) {
+        const int op = phase ? n_pad - 1 - p : p, opp = phase ? n_pad - 1 - pp : pp;
+        if (op < n && opp < n) {
+          if (phase == 0) {
+            v = T[(long long)opp + (long long)op * ldt];
+            v.y = -v.y;
+          } else {
+            v = T[(long long)op + (long long)opp * ldt];
+          }
+        } else if (p == pp) {
+          v.x = 1.0;
+        }
+      }
+      out[((kk >> 2) * 8 + (m >> 3)) * 32 + (m & 7) * 4 + (kk & 3)] = v;
+    }
+  }
+}
+
+// ---- the solve kernel ---------------------------------------------------------------------------------
+struct SolveParams {
+  const double2* packA;
+  const double2* packB;
+  int n, n_pad, nblk;
+  const int* active;   // slot ids, padded to a multiple of NS with the scratch slot
+  const int* n_active; // device scalar
+  double2* Q0;         // [W+1][n_pad]
+  double2* Q1;
+  double2* Wv;
+  const int* sel;      // which of Q0/Q1 currently holds q
+  const double2* z;    // per-slot shift
+};
+
+struct StepCursor {
+  int phase, I, c;
+  __device__ __forceinline__ void advance() {
+    if (++c == CPB * I + CPB) {
+      c = 0;
+      ++I;
+    }
+  }
+};
+
+// One CTA = one panel of NS shifts; 8 warps arranged 4 (M) x 2 (N): warp tile 16 rows x 32 shifts.
+// Left-looking block forward substitution (both phases, see pack_kernel): for block row I
+//   acc = sum_{c < 4I} L[I][c] * X[c]              (GEMM steps: T tile + X tile through the bulk-copy ring)
+//   for cp = 0..3: rows 16cp..16cp+15:  x = (L_dd - z)^{-1} (rhs - acc)   (diag step, per-shift, in registers)
+//                  acc += L[I][4I+cp] * x           (rows below, same DMMA code)
+__global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_kernel(SolveParams P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int n_active = *P.n_active;
+  const int panel = blockIdx.x;
+  if (panel * NS >= n_active) return;
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // 32 B reserved
+  double2* zsh = reinterpret_cast<double2*>(smem + STAGES * STAGE_BYTES + 32);    // 16 B aligned
+  double2** wptr = reinterpret_cast<double2**>(zsh + NS);
+  const double2** qptr = (const double2**)(wptr + NS);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp & 3, wn = warp >> 2;
+
+  if (tid < NS) {
+    const int slot = P.active[panel * NS + tid];
+    wptr[tid] = P.Wv + (size_t)slot * P.n_pad;
+    qptr[tid] = (P.sel[slot] ? P.Q1 : P.Q0) + (size_t)slot * P.n_pad;
+    zsh[tid] = P.z[slot];
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int nblk = P.nblk, n_pad = P.n_pad, n = P.n;
+  const int steps_per_phase = (int)tiles_per_phase(nblk);
+  const int total_steps = 2 * steps_per_phase;
+
+  // producer side: issue the loads of one step into its ring stage (called by warp 0 only)
+  auto issue = [&](const StepCursor& pc, int stage) {
+    unsigned char* sb = smem + stage * STAGE_BYTES;
+    const bool needX = pc.c < CPB * pc.I;
+    if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], TILE_BYTES + (needX ? NS * KC * 16 : 0));
+    __syncwarp();
+    if (lane == 0) {
+      const double2* src = (pc.phase ? P.packB : P.packA) + tile_index(pc.I, pc.c) * TILE_ELEMS;
+      bulk_g2s(sb, src, TILE_BYTES, &full_bar[stage]);
+    }
+    if (needX) {
+      const int mem0 = pc.phase ? n_pad - KC * pc.c - KC : KC * pc.c;
+#pragma unroll
+      for (int s = lane; s < NS; s += 32)
+        bulk_g2s(sb + TILE_BYTES + s * XROW_BYTES, wptr[s] + mem0, KC * 16, &full_bar[stage]);
+    }
+  };
+
+  double cre[2][4][2], cim[2][4][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) cre[a][b][0] = cre[a][b][1] = cim[a][b][0] = cim[a][b][1] = 0.0;
+
+  auto gemm_step = [&](const unsigned char* sb, int flip) {
+    const double2* At = reinterpret_cast<const double2*>(sb);
+    const unsigned char* Xt = sb + TILE_BYTES + (32 * wn + (lane >> 2)) * XROW_BYTES;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double2 a[2], b[4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) a[mt] = At[(j * 8 + 2 * wm + mt) * 32 + lane];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        b[nt] = *reinterpret_cast<const double2*>(Xt + nt * 8 * XROW_BYTES + (((4 * j + (lane & 3)) ^ flip) << 4));
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(cre[mt][nt][0], cre[mt][nt][1], a[mt].x, b[nt].x);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(cim[mt][nt][0], cim[mt][nt][1], a[mt].x, b[nt].y);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const double nai = -a[mt].y;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(cre[mt][nt][0], cre[mt][nt][1], nai, b[nt].y);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(cim[mt][nt][0], cim[mt][nt][1], a[mt].y, b[nt].x);
+    }
+  };
+
+  StepCursor cons{0, 0, 0}, prod{0, 0, 0};
+  auto advance_prod = [&]() {
+    prod.advance();
+    if (prod.I == nblk) prod = StepCursor{1, 0, 0};
+  };
+  if (warp == 0) {
+    for (int s = 0; s < STAGES && s < total_steps; ++s) {
+      issue(prod, s);
+      advance_prod();
+    }
+  }
+
+  for (int t = 0; t < total_steps; ++t) {
+    const int stage = t % STAGES;
+    const uint32_t parity = (uint32_t)(t / STAGES) & 1u;
+    unsigned char* sb = smem + stage * STAGE_BYTES;
+    const int flip = cons.phase ? (KC - 1) : 0;
+    mbar_wait(&full_bar[stage], parity);
+
+    if (cons.c < CPB * cons.I) {
+      gemm_step(sb, flip);
+    } else {
+      const int cp = cons.c - CPB * cons.I;  // diagonal sub-chunk 0..3
+      if (wm == cp) {
+        // this warp owns rows 16cp..16cp+15 of the block row for its 32 shifts: finish them.
+        const int s = 32 * wn + lane;
+        const int mem0 = cons.phase ? n_pad - KC * cons.c - KC : KC * cons.c;
+        const double2* rp = (cons.phase ? (const double2*)wptr[s] : qptr[s]) + mem0;
+        double2 b[KC];  // indexed by processing row r; memory / smem position is r ^ flip
+#pragma unroll
+        for (int r = 0; r < KC; ++r) b[r] = rp[r ^ flip];
+        unsigned char* Xt = sb + TILE_BYTES;
+        // transpose the accumulators through smem: element (row r, shift sl) -> Xt[sl][r ^ flip]
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int r = 8 * mt + (lane >> 2), sl = 32 * wn + 8 * nt + 2 * (lane & 3) + e;
+              *reinterpret_cast<double2*>(Xt + sl * XROW_BYTES + ((r ^ flip) << 4)) =
+                  make_double2(cre[mt][nt][e], cim[mt][nt][e]);
+              cre[mt][nt][e] = 0.0;
+              cim[mt][nt][e] = 0.0;
+            }
+        __syncwarp();
+        double2* xrow = reinterpret_cast<double2*>(Xt + s * XROW_BYTES);
+#pragma unroll
+        for (int r = 0; r < KC; ++r) {
+          const double2 a = xrow[r ^ flip];
+          b[r].x -= a.x;
+          b[r].y -= a.y;
+        }
+        const double2* At = reinterpret_cast<const double2*>(sb);
+        double2 zt = zsh[s];
+        if (cons.phase == 0) zt.y = -zt.y;  // adjoint system: diagonal conj(t_ii - z)
+        const int p0 = MB * cons.I + KC * cp;
+#pragma unroll
+        for (int r = 0; r < KC; ++r) {  // forward substitution in processing order
+          const int m = KC * cp + r;
+          double2 d = At[((r >> 2) * 8 + (m >> 3)) * 32 + (m & 7) * 4 + (r & 3)];
+          d.x -= zt.x;
+          d.y -= zt.y;
+          double2 x = cmul(b[r], crecip(d));
+          const int op = cons.phase ? n_pad - 1 - (p0 + r) : p0 + r;
+          if (op >= n) x = make_double2(0.0, 0.0);
+          b[r] = x;
+#pragma unroll
+          for (int r2 = r + 1; r2 < KC; ++r2) {
+            const int m2 = KC * cp + r2;
+            const double2 l = At[((r >> 2) * 8 + (m2 >> 3)) * 32 + (m2 & 7) * 4 + (r & 3)];
+            cmsub(b[r2], l, x);
+          }
+        }
+        double2* op_ = wptr[s] + mem0;
+#pragma unroll
+        for (int r = 0; r < KC; ++r) {
+          xrow[r ^ flip] = b[r];
+          op_[r ^ flip] = b[r];
+        }
+        fence_proxy_async();  // the next block rows read these x through the async proxy
+      }
+      __syncthreads();
+      if (wm > cp) gemm_step(sb, flip);
+    }
+    __syncthreads();  // every warp is done with this stage: refill it
+    if (warp == 0 && t + STAGES < total_steps) {
+      issue(prod, stage);
+      advance_prod();
+    }
+    cons.advance();
+    if (cons.I == nblk) cons = StepCursor{1, 0, 0};
+  }
+}
+
+// ---- scheduler: refill idle slots from the point queue, compact the active list -------------------------
+struct SchedParams {
+  int W;              // slot capacity (scratch slot has id W)
+  int P;              // points owned by this device
+  int rows_local;     // rows of the grid owned by this device
+  int row0, row_step; // global row of local row r: row0 + r*row_step
+  const double* x;    // lx
+  const double* y;    // ly (global)
+  int* slot_point;    // local point index or -1
+  double2* slot_z;
+  int* slot_iter;
+  double* slot_beta;
+  double* slot_sigold;
+  int* slot_sel;
+  int* active;        // out, padded with W to a multiple of NS
+  int* fresh;         // out, list of newly filled slots
+  int* state;         // [0]=next_point [1]=n_active [2]=n_fresh  (device)
+  int* host_state;    // mapped pinned mirror
+};
+
+__global__ void __launch_bounds__(1024) sched_kernel(SchedParams S) {
+  __shared__ int scan[1024];
+  __shared__ int base_s;
+  const int tid = threadIdx.x;
+  const int C = (S.W + 1023) / 1024;
+  const int lo = tid * C, hi = min(S.W, lo + C);
+  const int head = S.state[0];
+  auto exscan = [&](int v) -> int {  // exclusive scan over the block; total left in base_s
+    scan[tid] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int t = (tid >= o) ? scan[tid - o] : 0;
+      __syncthreads();
+      scan[tid] += t;
+      __syncthreads();
+    }
+    if (tid == 1023) base_s = scan[1023];
+    const int ex = scan[tid] - v;
+    __syncthreads();
+    return ex;
+  };
+  int idle = 0;
+  for (int i = lo; i < hi; ++i) idle += (S.slot_point[i] < 0);
+  int rank = exscan(idle);
+  const int total_idle = base_s;
+  __syncthreads();
+  const int n_fresh = max(0, min(total_idle, S.P - head));
+  for (int i = lo; i < hi; ++i) {
+    if (S.slot_point[i] < 0) {
+      const int p = head + rank;
+      if (p < S.P) {
+        const int jr = p % S.rows_local, k = p / S.rows_local;
+        const int j = S.row0 + jr * S.row_step;
+        S.slot_point[i] = p;
+        S.slot_z[i] = make_double2(S.x[k], S.y[j]);
+        S.slot_iter[i] = 0;
+        S.slot_beta[i] = 0.0;
+        S.slot_sigold[i] = 0.0;
+        S.slot_sel[i] = 0;
+        S.fresh[rank] = i;
+      }
+      ++rank;
+    }
+  }
+  int act = 0;
+  for (int i = lo; i < hi; ++i) act += (S.slot_point[i] >= 0);
+  int arank = exscan(act);
+  const int n_active = base_s;
+  for (int i = lo; i < hi; ++i)
+    if (S.slot_point[i] >= 0) S.active[arank++] = i;
+  const int padded = (n_active + NS - 1) / NS * NS;
+  for (int i = n_active + tid; i < padded; i += 1024) S.active[i] = S.W;
+  if (tid == 0) {
+    S.state[0] = head + n_fresh;
+    S.state[1] = n_active;
+    S.state[2] = n_fresh;
+    S.host_state[0] = head + n_fresh;
+    S.host_state[1] = n_active;
+    S.host_state[2] = n_fresh;
+    __threadfence_system();
+  }
+}
+
+// q <- q0 for freshly filled slots (qold needs no init: its first use is multiplied out, see lanczos_kernel)
+__global__ void init_fresh_kernel(const int* __restrict__ fresh, int n_pad, int n, const double2* __restrict__ q0,
+                                  double2* __restrict__ Q0) {
+  const int slot = fresh[blockIdx.x];
+  double2* q = Q0 + (size_t)slot * n_pad;
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) q[i] = (i < n) ? q0[i] : make_double2(0.0, 0.0);
+}
+
+// ---- largest eigenvalue of the l x l Lanczos tridiagonal, one warp, 32-way multisection Sturm counts ---
+// Stands in for `maximum(eigvals(H[1:l,1:l]))` (compute.jl:640-642).  d[], e2[] are in shared memory and
+// scaled to unit max-norm (e2 = squared off-diagonals), so nothing can overflow.
+__device__ __forceinline__ int sturm_count(int l, const double* d, const double* e2, double x) {
+  double q = d[0] - x;
+  if (q == 0.0) q = -1e-300;
+  int cnt = q < 0.0;
+  for (int i = 1; i < l; ++i) {
+    q = d[i] - x - e2[i - 1] / q;
+    if (q == 0.0) q = -1e-300;
+    cnt += q < 0.0;
+  }
+  return cnt;  // eigenvalues < x
+}
+
+__device__ double tridiag_max_eig_warp(int l, const double* d, const double* e2, int lane) {
+  if (l == 1) return d[0];
+  double lo = -1e300, hi = -1e300;
+  for (int i = 0; i < l; ++i) {
+    const double el = i > 0 ? sqrt(e2[i - 1]) : 0.0, er = i + 1 < l ? sqrt(e2[i]) : 0.0;
+    lo = fmax(lo, d[i]);            // lambda_max >= max diagonal  => count(lo) < l
+    hi = fmax(hi, d[i] + el + er);  // Gershgorin
+  }
+  hi += 4e-16 * fmax(fabs(hi), 1.0);  // count(hi) == l
+  for (int round = 0; round < 16; ++round) {
+    const double w = hi - lo;
+    const double x = lo + w * ((double)(lane + 1) / 33.0);
+    const bool ok = sturm_count(l, d, e2, x) >= l;
+    const unsigned mask = __ballot_sync(0xffffffffu, ok);
+    double nlo, nhi;
+    if (mask == 0u) {
+      nlo = __shfl_sync(0xffffffffu, x, 31);
+      nhi = hi;
+    } else {
+      const int f = __ffs(mask) - 1;
+      nhi = __shfl_sync(0xffffffffu, x, f);
+      const double below = __shfl_sync(0xffffffffu, x, f > 0 ? f - 1 : 0);
+      nlo = f > 0 ? below : lo;
+    }
+    lo = nlo;
+    hi = nhi;
+    if (hi - lo <= 4.5e-16 * fmax(fabs(lo), fabs(hi))) break;
+  }
+  return 0.5 * (lo + hi);
+}
+
+// ---- fused Lanczos recurrence + convergence test ------------------------------------------------------
+// One CTA per active shift.  compute.jl:630-661:  v -= beta*qold; alpha = Re(q.v); v -= alpha q; beta = |v|;
+// qold = q; q = v/beta; sigma = max eig(H_l); stop on |sigold/sigma - 1| < tol or beta == 0.
+struct LanczosParams {
+  int n, n_pad, W;
+  const int* active;
+  const int* n_active;
+  double2* Q0;
+  double2* Q1;
+  double2* Wv;
+  int* slot_point;
+  int* slot_iter;
+  double* slot_beta;
+  double* slot_sigold;
+  int* slot_sel;
+  double* hist_alpha;  // [W][HIST]
+  double* hist_beta;
+  double tol;
+  int maxit;
+  double bigsigma;
+  double* Z;          // local point order
+  int* iters;         // nullable
+  unsigned long long* counts;  // PSA_COUNT_*
+};
+
+constexpr int LZ_THREADS = 256;
+
+__global__ void __launch_bounds__(LZ_THREADS) lanczos_kernel(LanczosParams L) {
+  __shared__ double red[LZ_THREADS / 32];
+  __shared__ double sd[HIST], se2[HIST];
+  __shared__ double s_sigma;
+  if ((int)blockIdx.x >= *L.n_active) return;
+  const int slot = L.active[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int n = L.n;
+  const int sel = L.slot_sel[slot];
+  double2* q = (sel ? L.Q1 : L.Q0) + (size_t)slot * L.n_pad;
+  double2* qold = (sel ? L.Q0 : L.Q1) + (size_t)slot * L.n_pad;
+  double2* w = L.Wv + (size_t)slot * L.n_pad;
+  const int l = L.slot_iter[slot] + 1;
+  const double beta_old = L.slot_beta[slot];
+
+  // v = w - beta*qold ; alpha = Re(q . v)
+  double part = 0.0;
+  for (int i = tid; i < n; i += LZ_THREADS) {
+    double2 v = w[i];
+    if (l > 1) {
+      const double2 o = qold[i];
+      v.x -= beta_old * o.x;
+      v.y -= beta_old * o.y;
+      w[i] = v;
+    }
+    const double2 qq = q[i];
+    part = fma(qq.x, v.x, part);
+    part = fma(qq.y, v.y, part);
+  }
+  const double alpha = block_sum<LZ_THREADS>(part, red);
+  // v -= alpha q ; beta = |v|
+  part = 0.0;
+  for (int i = tid; i < n; i += LZ_THREADS) {
+    double2 v = w[i];
+    const double2 qq = q[i];
+    v.x -= alpha * qq.x;
+    v.y -= alpha * qq.y;
+    w[i] = v;
+    part = fma(v.x, v.x, part);
+    part = fma(v.y, v.y, part);
+  }
+  double ss = block_sum<LZ_THREADS>(part, red);
+  double beta;
+  if (isfinite(ss) && ss > 1e-280) {
+    beta = sqrt(ss);
+  } else {  // scaled 2-norm (the reference's norm() is BLAS dznrm2, which cannot overflow prematurely)
+    double mx = 0.0;
+    for (int i = tid; i < n; i += LZ_THREADS) {
+      const double2 v = w[i];
+      mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+    }
+    mx = block_max<LZ_THREADS>(mx, red);
+    if (mx == 0.0 || !isfinite(mx)) {
+      beta = mx == 0.0 ? 0.0 : ss;  // 0, or inf/nan propagated
+    } else {
+      part = 0.0;
+      for (int i = tid; i < n; i += LZ_THREADS) {
+        const double2 v = w[i];
+        const double a = v.x / mx, b = v.y / mx;
+        part = fma(a, a, part);
+        part = fma(b, b, part);
+      }
+      beta = mx * sqrt(block_sum<LZ_THREADS>(part, red));
+    }
+  }
+  // qold <- q (buffer swap), q <- v / beta (written over the old qold buffer)
+  for (int i = tid; i < n; i += LZ_THREADS) {
+    const double2 v = w[i];
+    qold[i] = make_double2(v.x / beta, v.y / beta);
+  }
+
+  double* ha = L.hist_alpha + (size_t)slot * HIST;
+  double* hb = L.hist_beta + (size_t)slot * HIST;
+  const bool finite_ab = isfinite(alpha) && isfinite(beta);
+  if (tid == 0) {
+    ha[l - 1] = alpha;
+    hb[l - 1] = beta;
+  }
+  // scaled copy of H[1:l,1:l] into shared memory
+  double mx = 0.0;
+  if (finite_ab) {
+    for (int i = tid; i < l; i += LZ_THREADS) {
+      const double a = (i == l - 1) ? alpha : ha[i];
+      mx = fmax(mx, fabs(a));
+      if (i < l - 1) mx = fmax(mx, fabs(hb[i]));
+    }
+  }
+  mx = block_max<LZ_THREADS>(mx, red);
+  if (finite_ab && mx > 0.0) {
+    for (int i = tid; i < l; i += LZ_THREADS) {
+      const double a = (i == l - 1) ? alpha : ha[i];
+      sd[i] = a / mx;
+      if (i < l - 1) {
+        const double b = hb[i] / mx;
+        se2[i] = b * b;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    double sigma;
+    bool failed = false;
+    if (!finite_ab) {
+      sigma = L.bigsigma;
+      failed = true;
+    } else if (mx == 0.0) {
+      sigma = 0.0;
+    } else {
+      sigma = mx * tridiag_max_eig_warp(l, sd, se2, tid);
+    }
+    if (tid == 0) {
+      const double sigold = L.slot_sigold[slot];
+      const bool conv = !failed && (fabs(sigold / sigma - 1.0) < L.tol || beta == 0.0);
+      if (conv || failed || l >= L.maxit) {
+        const int p = L.slot_point[slot];
+        L.Z[p] = 1.0 / sqrt(sigma);
+        if (L.iters) L.iters[p] = l;
+        L.slot_point[slot] = -1;
+        if (!conv && !failed) atomicAdd(&L.counts[0], 1ull);
+        if (failed) atomicAdd(&L.counts[1], 1ull);
+        atomicAdd(&L.counts[2], (unsigned long long)l);
+        atomicAdd(&L.counts[3], 1ull);
+      } else {
+        L.slot_sigold[slot] = sigma;
+        L.slot_iter[slot] = l;
+        L.slot_beta[slot] = beta;
+        L.slot_sel[slot] = sel ^ 1;
+      }
+    }
+  }
+}
+
+// ---- helpers for the apply_resolvent diagnostic hook ---------------------------------------------------
+__global__ void load_slots_kernel(int ns, int n, int n_pad, const double2* __restrict__ Q, const double2* __restrict__ z,
+                                  double2* __restrict__ Q0, double2* __restrict__ slot_z, int* __restrict__ slot_sel,
+                                  int* __restrict__ active, int W, int* __restrict__ state) {
+  const int s = blockIdx.x;
+  if (s < ns) {
+    double2* q = Q0 + (size_t)s * n_pad;
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) q[i] = (i < n) ? Q[(size_t)s * n + i] : make_double2(0.0, 0.0);
+    if (threadIdx.x == 0) {
+      slot_z[s] = z[s];
+      slot_sel[s] = 0;
+      active[s] = s;
+    }
+  } else if (threadIdx.x == 0) {
+    active[s] = W;
+  }
+  if (s == 0 && threadIdx.x == 0) state[1] = ns;
+}
+
+__global__ void store_slots_kernel(int n, int n_pad, const double2* __restrict__ Wv, double2* __restrict__ V) {
+  const int s = blockIdx.x;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) V[(size_t)s * n + i] = Wv[(size_t)s * n_pad + i];
+}
+
+}  // namespace psa
