@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- resolvent-norm grid points/s on the BASELINE workload (dense random complex n=4000 Schur factor,
+400x400 grid = BASELINE.json configs[2], the configuration the metric is quoted on; it fits one B200).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (default N=1)
+    python bench.py --impl reference ...                     # the reference algorithm on the host cores (C oracle port)
+
+A "step" is one pass of the hot path over the whole grid.  Under torchrun (N > 1) the computed rows are dealt
+cyclically over the ranks (strong scaling: the grid is fixed), T is broadcast once with NCCL and the sigma_min
+tiles are gathered on rank 0 inside the timed region.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "resolvent-norm grid points/sec"
+UNIT = "points/s"
+FP64_PEAK_FILE = os.path.join(ROOT, "profiles", "r01_fp64_gemm_peak.json")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---- workload -----------------------------------------------------------------------------------------------
+
+def build_workload(n: int, npts: int, seed: int = 1):
+    """A = N(0,1) + i N(0,1) (default_rng(seed)); T = complex Schur factor (the reference's one-time host
+    LinearAlgebra call, src/Pseudospectra.jl:206-213), timed separately and cached under /tmp."""
+    import scipy.linalg as sla
+    cache = os.path.join(os.environ.get("PSA_BENCH_CACHE", "/tmp/psa_b200_cache"), f"schur_n{n}_seed{seed}.npy")
+    t0 = time.time()
+    if os.path.exists(cache):
+        T = np.load(cache)
+        how = "cached"
+    else:
+        rng = np.random.default_rng(seed)
+        A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        T, _ = sla.schur(A, output="complex")
+        T = np.triu(T)
+        try:
+            os.makedirs(os.path.dirname(cache), exist_ok=True)
+            np.save(cache + ".tmp.npy", T)
+            os.replace(cache + ".tmp.npy", cache)
+        except OSError:
+            pass
+        how = "computed"
+    schur_s = time.time() - t0
+    T = np.asfortranarray(T)
+    return T, schur_s, how
+
+
+def grid_for(T, npts, pkg):
+    from pseudospectra_jl_b200 import compute as hc
+    ax = pkg.vec2ax(np.diagonal(T))
+    x, y, _ = hc._grid(ax, npts, False, False)
+    return ax, x, y
+
+
+def start_vector(n, seed=0):
+    rng = np.random.default_rng(seed)
+    q = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    return q / np.linalg.norm(q)
+
+
+# ---- clocks -------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- CPU arm (reference algorithm on host cores) -------------------------------------------------------------
+
+def cpu_sample_points(x, y, count):
+    """A bounded, evenly strided sample of the grid: `count` points as a (rows x cols) sub-grid."""
+    r = max(1, int(round(np.sqrt(count))))
+    jj = np.linspace(0, len(y) - 1, r).round().astype(int)
+    kk = np.linspace(0, len(x) - 1, max(1, count // r)).round().astype(int)
+    return x[kk], y[jj]
+
+
+def cpu_arm(T, x, y, q0, target_s, threads):
+    """Times oracle/psa_oracle.c (threaded restatement of src/compute.jl:534-562) on a bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle as co
+    xs, ys = cpu_sample_points(x, y, threads)  # calibration: one point per thread
+    t0 = time.time()
+    co.grid(T, xs, ys, q0, nthreads=threads)
+    t_cal = max(time.time() - t0, 1e-3)
+    per_round = len(xs) * len(ys)
+    count = int(min(len(x) * len(y), max(per_round, per_round * target_s / t_cal)))
+    xs, ys = cpu_sample_points(x, y, count)
+    t0 = time.time()
+    Z, it, fl = co.grid(T, xs, ys, q0, nthreads=threads)
+    dt = time.time() - t0
+    npnt = len(xs) * len(ys)
+    return {"value": npnt / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{len(ys)}x{len(xs)} evenly strided sub-grid ({npnt} points, {dt:.1f} s, mean {it.mean():.1f} "
+                      f"Lanczos iterations) of the same workload; C restatement of the reference's Threads path "
+                      f"(Julia is not installed), one worker thread per host core"}, npnt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    psa_b200 = __import__("psa_b200_loader").load_package()
+    T, schur_s, how = build_workload(args.n, args.npts)
+    ax, x, y = grid_for(T, args.npts, psa_b200)
+    q0 = start_vector(args.n)
+    threads = os.cpu_count() or 1
+    per_step_s = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_arm(T, x, y, q0, per_step_s / 4, threads)
+    tot_p, tot_t, last = 0, 0.0, None
+    for _ in range(args.steps):
+        last, npnt, dt = cpu_arm(T, x, y, q0, per_step_s, threads)
+        tot_p += npnt
+        tot_t += dt
+    val = tot_p / tot_t
+    last["value"] = val
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(args, ax), "cpu_baseline": last,
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "schur_s": schur_s, "schur": how}
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+def workload_config(args, ax):
+    return {"workload": f"dense random complex n={args.n} (default_rng(1)) complex Schur factor, {args.npts}x{args.npts} grid "
+                        f"on ax=vec2ax(eigenvalues); BASELINE.json configs[2]", "n": args.n, "grid": [args.npts, args.npts],
+            "ax": ax, "tol": 1e-5, "maxit": 99, "q0": "normalize(randn+i*randn), default_rng(0)",
+            "parallelism": f"grid rows dealt cyclically over {args.gpus} rank(s); T broadcast once (NCCL); Z gathered on rank 0",
+            "l2": "inputs larger than L2: packed T is 2 x %.0f MB, re-streamed every scheduler tick" % (
+                16e-6 * 2 * ((args.n + 63) // 64) * ((args.n + 63) // 64 + 1) * 1024)}
+
+
+# ---- GPU arm ----------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = __import__("psa_b200_loader").load_package()
+    from pseudospectra_jl_b200 import sharding
+
+    n, npts = args.n, args.npts
+    # one-time host reduction on rank 0, then NCCL broadcast of T (column-major storage)
+    T_host = torch.empty((n, n), dtype=torch.complex128).pin_memory()  # holds T^T row-major == T column-major
+    schur_s, how = 0.0, "broadcast"
+    if rank == 0:
+        T, schur_s, how = build_workload(n, npts)
+        T_host.copy_(torch.from_numpy(T.T))
+        log(f"[bench] schur {how} in {schur_s:.1f} s")
+    T_dev = torch.empty((n, n), dtype=torch.complex128, device=dev)
+    t0 = time.time()
+    if rank == 0:
+        T_dev.copy_(T_host, non_blocking=True)
+    sharding.broadcast_matrix(T_dev, 0)
+    torch.cuda.synchronize()
+    bcast_s = time.time() - t0
+    if rank != 0:
+        T_host.copy_(T_dev)  # every rank keeps a pinned host copy for its end-to-end leg
+    T_np = T_host.numpy().T  # column-major view (n x n)
+    ax, x, y = grid_for(T_np, npts, pkg)
+    q0 = start_vector(n)
+    rows = sharding.rows_for_rank(len(y), rank, world)
+    y_loc = np.ascontiguousarray(y[rows])
+    lx, lyl = len(x), len(y_loc)
+
+    ctx = pkg.PsaGpu(device_ids=[local_rank])
+    ctx.set_matrix_device(T_dev.data_ptr(), n, n, n)
+    d_x = torch.from_numpy(x).to(dev)
+    d_y = torch.from_numpy(y_loc).to(dev)
+    d_q0 = torch.view_as_real(torch.from_numpy(q0).to(dev)).contiguous()
+    d_Z = torch.empty((lx, lyl), dtype=torch.float64, device=dev)      # column-major (lyl x lx)
+    d_it = torch.empty((lx, lyl), dtype=torch.int32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stats_acc = {"solve_ms": 0.0, "solve_launches": 0.0, "total_launches": 0.0, "flops": 0.0, "grid_ms": 0.0, "ticks": 0.0}
+    state = {}
+
+    def step_resident(acc):
+        counts, algo = ctx.grid_device(d_x.data_ptr(), lx, d_y.data_ptr(), lyl, d_q0.data_ptr(), d_Z.data_ptr(),
+                                       d_it.data_ptr())
+        Zfull = sharding.gather_rows(d_Z.t(), len(y), lx, 0)  # NCCL gather of the sigma_min tiles to rank 0
+        if acc:
+            st = ctx.last_stats()
+            for k in stats_acc:
+                stats_acc[k] += st[k]
+        state["counts"], state["algo"], state["Z"] = counts, algo, Zfull
+
+    for _ in range(args.warmup):
+        step_resident(False)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident(True)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    counts = torch.tensor(np.asarray(state["counts"], dtype=np.float64), device=dev)
+    if world > 1:
+        dist.all_reduce(counts)
+    counts = counts.cpu().numpy()
+    points = int(len(x) * len(y))
+
+    # ---- end-to-end leg: the public host-array call (set_matrix + grid), H2D/D2H inside the timed region ----
+    Z_host = None
+
+    def step_e2e():
+        nonlocal Z_host
+        ctx.set_matrix(T_np)                                   # H2D of T from pinned host memory + packing
+        Zl, itl, c, algo = ctx.grid(x, y_loc, q0)              # H2D x, y, q0; D2H Z, iters
+        Zt = torch.from_numpy(np.ascontiguousarray(Zl)).to(dev)
+        Zf = sharding.gather_rows(Zt, len(y), lx, 0)
+        if rank == 0:
+            Z_host = Zf.cpu().numpy()
+
+    e2e_steps = max(1, args.steps if args.e2e_steps is None else args.e2e_steps)
+    step_e2e()  # warm-up
+    barrier()
+    t0 = time.time()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(e2e_steps):
+        step_e2e()
+    f1.record()
+    barrier()
+    ems = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ems.item()) / e2e_steps
+    h2d = n * n * 16 + (lx + lyl) * 8 + n * 16
+    d2h = lx * lyl * (8 + 4)
+
+    if rank == 0:
+        # parity spot-check of the e2e result against the resident result (same inputs -> bitwise equal)
+        Zr = state["Z"].cpu().numpy()
+        same = bool(np.array_equal(Zr, Z_host))
+        peak = {"zgemm": {"sustained_tflops": 36.7, "burst_tflops": 36.8}}
+        try:
+            peak = json.load(open(FP64_PEAK_FILE))
+        except OSError:
+            pass
+        solve_ms_avg = stats_acc["solve_ms"] / max(stats_acc["solve_launches"], 1)
+        flops_per_launch = stats_acc["flops"] / max(stats_acc["solve_launches"], 1)
+        achieved = flops_per_launch / (solve_ms_avg * 1e-3) * 1e-12 if solve_ms_avg > 0 else 0.0
+        pk = peak["zgemm"]["sustained_tflops"]
+        out = {
+            "metric": METRIC, "value": points * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, ax),
+            "clocks": clocks,
+            "e2e": {"value": points / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms, "bitwise_equal_to_resident": same,
+                    "call": "PsaGpu.set_matrix(T_host) + PsaGpu.grid(x, y, q0) per rank (C ABI psa_gpu_set_matrix + psa_gpu_grid)"},
+            "gpu_launches": int(stats_acc["total_launches"]),
+            "roofline": {"bound": "tensor", "kernel": "psa::solve_kernel (FP64 DMMA multi-shift triangular solves)",
+                         "achieved": achieved, "peak": pk, "unit": "TFLOP/s", "frac": achieved / pk,
+                         "peak_source": "measured on this pool: cuBLAS ZGEMM 4096^3 sustained, profiles/r01_fp64_gemm_peak.json "
+                                        "(MEASURED_PEAKS.json holds no FP64 figure; raw DMMA issue peak 37.2)",
+                         "flops_per_launch": flops_per_launch, "ms_per_launch": solve_ms_avg,
+                         "solve_share_of_step": stats_acc["solve_ms"] / max(stats_acc["grid_ms"], 1e-9),
+                         "whole_step_tflops": stats_acc["flops"] / (ms_total * 1e-3) * 1e-12, "traffic": None},
+            "lanczos": {"mean_iters": float(counts[2] / max(counts[3], 1)), "nonconverged": int(counts[0]),
+                        "fallback": int(counts[1]), "ticks_per_step": stats_acc["ticks"] / args.steps},
+            "schur_s": schur_s, "schur": how, "bcast_s": bcast_s, "algo": state["algo"],
+        }
+        if world == 1 and not args.no_cpu:
+            cb, _, _ = cpu_arm(T_np, x, y, q0, args.cpu_seconds, os.cpu_count() or 1)
+            out["cpu_baseline"] = cb
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=4000, help="matrix size (default: the BASELINE workload)")
+    ap.add_argument("--npts", type=int, default=400)
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

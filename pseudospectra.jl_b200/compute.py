@@ -176,6 +176,29 @@ def recalc_levels(sigmin, ax):
     return levels, 0
 
 
+def tidyaxes(vmin, vmax, tol):
+    """src/utils.jl:237-248"""
+    round_to = (vmax - vmin) * tol
+    expon = math.floor(math.log10(round_to))
+    round_to = round(10 ** (math.log10(round_to) - expon)) * 10.0 ** expon
+    return round_to * math.floor(vmin / round_to), round_to * math.ceil(vmax / round_to)
+
+
+def vec2ax(dispvec):
+    """Axis limits around the eigenvalues, as spectralportrait does (src/utils.jl:175-191, src/Pseudospectra.jl:729)."""
+    v = np.asarray(dispvec)
+    ca = [float(v.real.min()), float(v.real.max()), float(v.imag.min()), float(v.imag.max())]
+    if ca[0] == ca[1]:
+        ca[0], ca[1] = ca[0] - 0.5, ca[1] + 0.5
+    if ca[2] == ca[3]:
+        ca[2], ca[3] = ca[2] - 0.5, ca[3] + 0.5
+    ext = max(ca[1] - ca[0], ca[3] - ca[2]) / 3
+    ax = [ca[0] - ext, ca[1] + ext, ca[2] - ext, ca[3] + ext]
+    ax[0], ax[1] = tidyaxes(ax[0], ax[1], 0.02)
+    ax[2], ax[3] = tidyaxes(ax[2], ax[3], 0.02)
+    return [float(a) for a in ax]
+
+
 def psa_compute(Targ, npts, ax, eigA, opts=None, S=None, *, psatol=1e-5, thresholds=_default_thresholds,
                 ctrlflag=None, q0=None, rng=None, ngpus=1, ctx: PsaGpu | None = None):
     """psa_compute(T,npts,ax,eigA,opts,S=I) -> (Z,x,y,levels,info,Tproj,eigAproj,algo)   [src/compute.jl:87-268]

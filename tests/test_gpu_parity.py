@@ -1,0 +1,207 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the CPU oracle on
+identical (T, x, y, q0) and against the committed golden vectors.  Tolerance: sigma_min within 1e-6 relative of the
+oracle (north_star); iteration counts identical up to rounding-level ties at the stopping threshold."""
+import math
+
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+import c_oracle as co
+import psa_oracle as po
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6  # north_star: sigma_min within 1e-6 relative
+
+
+@pytest.fixture(scope="module")
+def gpu(pkg):
+    g = pkg.PsaGpu(1)
+    yield g
+    g.close()
+
+
+def _floor(T):
+    """sigma_min is only defined to about n*eps*||T||; the 1e-6 relative bar applies above this floor."""
+    return 1e-9 * float(np.linalg.norm(T))
+
+
+def _rel(Z, Zref, floor=1e-13):
+    ok = Zref > floor
+    return float(np.max(np.abs(Z[ok] - Zref[ok]) / Zref[ok])) if ok.any() else 0.0
+
+
+@pytest.mark.parametrize("n,ns", [(64, 1), (100, 64), (150, 70), (192, 5), (333, 130)])
+def test_solve_kernel_matches_triangular_solves(gpu, n, ns):
+    """One application of v = F1 \\ (F1' \\ q) (compute.jl:630) for ns shifts at once vs LAPACK ztrtrs."""
+    rng = np.random.default_rng(n + ns)
+    T = np.triu(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) + np.diag(3 * rng.standard_normal(n))
+    z = 5 * (rng.standard_normal(ns) + 1j * rng.standard_normal(ns))
+    Q = rng.standard_normal((ns, n)) + 1j * rng.standard_normal((ns, n))
+    gpu.set_matrix(T)
+    V = gpu.apply_resolvent(z, Q)
+    for s in range(ns):
+        F = T - z[s] * np.eye(n)
+        v = sla.solve_triangular(F, sla.solve_triangular(F, Q[s], trans="C"))
+        assert np.linalg.norm(V[s] - v) <= 1e-11 * np.linalg.norm(v)
+
+
+def test_solve_kernel_is_linear_and_ignores_strict_lower_part(gpu):
+    rng = np.random.default_rng(7)
+    n, ns = 200, 16
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))  # full matrix: i > j must be ignored
+    z = 4 * (rng.standard_normal(ns) + 1j * rng.standard_normal(ns))
+    Q1 = rng.standard_normal((ns, n)) + 1j * rng.standard_normal((ns, n))
+    Q2 = rng.standard_normal((ns, n)) + 1j * rng.standard_normal((ns, n))
+    gpu.set_matrix(A)
+    V1, V2, V12 = gpu.apply_resolvent(z, Q1), gpu.apply_resolvent(z, Q2), gpu.apply_resolvent(z, Q1 + 2j * Q2)
+    assert np.allclose(V12, V1 + 2j * V2, rtol=1e-10, atol=1e-12 * np.abs(V12).max())
+    gpu.set_matrix(np.triu(A))
+    assert np.array_equal(gpu.apply_resolvent(z, Q1), V1)  # UpperTriangular semantics, bit-exact
+
+
+def test_readme150_full_grid_vs_oracle(gpu):
+    """BASELINE config 1: README 150x150 banded matrix, default 100x100 grid, sq_lanc."""
+    T, eigA = po.complex_schur(po.readme_matrix(150))
+    x, y, _ = po.make_grid(po.vec2ax(eigA), 100, False)
+    q0 = po.start_vector(150, 0)
+    gpu.set_matrix(T)
+    Z, it, counts, algo = gpu.grid(x, y, q0)
+    Zc, itc, flc = co.grid(T, x, y, q0, nthreads=8)
+    assert algo == "sq_lanc"
+    assert _rel(Z, Zc) < RTOL
+    assert np.mean(it == itc) > 0.999
+    assert counts[3] == 10000 and counts[2] == it.sum() and counts[0] == 0 and counts[1] == 0
+
+
+def test_golden_readme_and_svd(gpu, golden):
+    g = golden("readme150")
+    gpu.set_matrix(g["T"])
+    Z, it, counts, algo = gpu.grid(g["x"], g["y"], g["q0"])
+    assert _rel(Z, g["Z"]) < RTOL and np.array_equal(it, g["iters"])
+    # no worse than the reference algorithm versus svdvals on sampled points
+    err_gpu = np.abs(Z - g["svd"]) / g["svd"]
+    err_ref = np.abs(g["Z"] - g["svd"]) / g["svd"]
+    assert err_gpu.max() <= err_ref.max() * 1.01 + 1e-9
+
+
+def test_real_matrix_mirror_through_psa_compute(pkg, golden):
+    """Real matrix -> shift_axes half grid + un-mirror + clamp; same tuple as the reference's psa_compute."""
+    g = golden("grcar120_real")
+    out = pkg.psa_compute(g["T"], 24, list(g["ax"]), np.diagonal(g["T"]), {"real_matrix": True}, q0=g["q0"])
+    Z, x, y, levels, err, Tproj, eigAproj, algo = out
+    assert algo == "sq_lanc" and err == 0 and Z.shape == g["Z"].shape
+    assert np.array_equal(x, g["x"]) and np.array_equal(y, g["y"])  # grid coordinates exact
+    assert _rel(Z, g["Z"], _floor(g["T"])) < RTOL
+    assert np.allclose(levels, g["levels"])
+    assert Z.min() >= 10 * math.sqrt(np.finfo(float).tiny)
+
+
+def test_hessqr_golden_medrect(gpu, golden):
+    """test/medrect.jl: grcar(210)[:,1:end-1] -> :HessQR."""
+    g = golden("hessqr210")
+    gpu.set_matrix(g["H"])
+    Z, it, counts, algo = gpu.grid(g["x"], g["y"], g["q0"])
+    assert algo == "HessQR"
+    assert _rel(Z, g["Z"], _floor(g["H"])) < RTOL
+    assert np.mean(it == g["iters"]) > 0.97
+
+
+def test_hessqr_arnoldi_projection_vs_oracle(gpu):
+    """BASELINE config 4 in miniature: convdiff_fd operator projected by Arnoldi -> (m+1) x m Hessenberg."""
+    A = po.convdiff_fd(6)
+    H = po.arnoldi_hessenberg(A, 208, seed=0)
+    ev = np.linalg.eigvals(H[:208, :])
+    x, y, _ = po.make_grid(po.vec2ax(ev), 14, False)
+    q0 = po.start_vector(208, 2)
+    gpu.set_matrix(H)
+    Z, it, counts, algo = gpu.grid(x, y, q0)
+    Zc, itc, flc = co.grid(np.asarray(H, dtype=complex), x, y, q0, nthreads=8)
+    assert algo == "HessQR" and _rel(Z, Zc, _floor(H)) < RTOL and np.mean(it == itc) > 0.97
+
+
+def test_random_complex_600_vs_oracle_and_svd(gpu):
+    T, eigA = po.complex_schur(po.random_complex(600, 1))
+    x, y, _ = po.make_grid(po.vec2ax(eigA), 40, False)
+    q0 = po.start_vector(600, 0)
+    gpu.set_matrix(T)
+    Z, it, counts, algo = gpu.grid(x, y, q0)
+    Zc, itc, _ = co.grid(T, x, y, q0, nthreads=8)
+    assert _rel(Z, Zc) < RTOL and np.mean(it == itc) > 0.999
+    for (j, k) in [(0, 0), (20, 20), (39, 5), (7, 31)]:
+        s = po.sigmin_svd(T, x[k] + 1j * y[j])
+        assert abs(Z[j, k] - s) / s <= abs(Zc[j, k] - s) / s * 1.01 + 1e-9
+
+
+def test_overflow_points_use_bigsigma_like_the_oracle(gpu):
+    """Strongly non-normal input: the solves overflow near the spectrum; both sides map that to bigsigma (then the
+    clamp to ps_tiny), and agree to 1e-6 wherever sigma_min is above rounding level."""
+    T, eigA = po.complex_schur(po.grcar(400))
+    x = np.linspace(0.2, 2.0, 10)
+    y = np.linspace(0.1, 2.5, 9)
+    q0 = po.start_vector(400, 0)
+    gpu.set_matrix(T)
+    Z, it, counts, algo = gpu.grid(x, y, q0)
+    Zc, itc, flc = co.grid(T, x, y, q0, nthreads=8)
+    assert _rel(Z, Zc, _floor(T)) < RTOL
+    fb_gpu, fb_cpu = Z < po.PS_TINY, (flc & 2) != 0
+    assert np.array_equal(fb_gpu, fb_cpu)
+    assert counts[1] == fb_cpu.sum()
+
+
+def test_edge_shapes_and_reuse(gpu):
+    """1x1 grid, ragged panel counts, n a multiple of the tile and not, matrix reuse across calls (zoom)."""
+    for n in (55, 64, 65, 128, 191):
+        T, _ = po.complex_schur(po.random_complex(n, n))
+        q0 = po.start_vector(n, 1)
+        gpu.set_matrix(T)
+        for lx, ly in ((1, 1), (65, 1), (3, 43)):
+            x, y = np.linspace(-1.5, 2.0, lx), np.linspace(-0.7, 1.1, ly)
+            Z, it, counts, algo = gpu.grid(x, y, q0)
+            Zc, itc, _ = co.grid(T, x, y, q0, nthreads=4)
+            assert Z.shape == (ly, lx) and _rel(Z, Zc) < RTOL and counts[3] == lx * ly
+        # zoom: second grid on the resident matrix
+        Z2, _, _, _ = gpu.grid(np.linspace(0.0, 0.5, 7), np.linspace(0.0, 0.5, 5), q0)
+        Zc2, _, _ = co.grid(T, np.linspace(0.0, 0.5, 7), np.linspace(0.0, 0.5, 5), q0)
+        assert _rel(Z2, Zc2) < RTOL
+
+
+def test_unsupported_shapes_raise(pkg, gpu):
+    with pytest.raises(pkg.PsaGpuUnsupported):
+        gpu.set_matrix(np.triu(np.ones((32, 32))))  # n < 55: SVD branch stays on the host (compute.jl:478)
+    with pytest.raises(pkg.PsaGpuUnsupported):
+        gpu.set_matrix(np.ones((190, 189)))  # m <= 200: rect_qr (compute.jl:588-590)
+    with pytest.raises(pkg.PsaGpuError):
+        pkg.PsaGpu(1).grid([0.0], [0.0], np.ones(4))  # no matrix set
+
+
+def test_cancel_flag_returns_none(pkg):
+    T, eigA = po.complex_schur(po.random_complex(300, 2))
+    flag = np.ones(1, dtype=np.int32)  # already cancelled: compute.jl:202-204 -> nothing
+    assert pkg.psa_compute(T, 30, [-20, 20, -20, 20], eigA, {}, ctrlflag=flag, q0=po.start_vector(300)) is None
+    flag[0] = 0
+    out = pkg.psa_compute(T, 6, [-20, 20, -20, 20], eigA, {}, ctrlflag=flag, q0=po.start_vector(300))
+    assert out is not None and out[0].shape == (6, 6)
+
+
+def test_maxit_nonconvergence_counted(gpu):
+    T, _ = po.complex_schur(po.random_complex(200, 3))
+    q0 = po.start_vector(200, 0)
+    gpu.set_matrix(T)
+    x, y = np.linspace(-10, 10, 9), np.linspace(-10, 10, 9)
+    Z, it, counts, _ = gpu.grid(x, y, q0, maxit=3)
+    Zc, itc, flc = co.grid(T, x, y, q0, maxit=3)
+    assert it.max() <= 3 and counts[0] == (flc & 1).sum() and _rel(Z, Zc) < RTOL
+
+
+def test_conjugate_symmetry_large_real_matrix(gpu):
+    """Size-independent property at a larger size: for a real matrix sigma_min(conj z) == sigma_min(z)."""
+    T, eigA = po.complex_schur(po.toeplitz_from_symbol([0.0, 1.0], [0.0, 0.0, 0.25], 1024))  # toeplitz.jl 'triangle'
+    x = np.linspace(-0.2, 1.4, 12)
+    y = np.array([0.31, 0.77, 1.3])
+    q0 = po.start_vector(1024, 0)
+    gpu.set_matrix(T)
+    Zp, _, _, _ = gpu.grid(x, y, q0)
+    Zm, _, _, _ = gpu.grid(x, -y, q0)
+    ok = Zp > 1e-9
+    assert np.allclose(Zp[ok], Zm[ok], rtol=2e-4)  # two independent Lanczos runs at tol 1e-5 (test/threads.jl:18 uses 1e-4)

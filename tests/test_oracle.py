@@ -1,0 +1,126 @@
+"""CPU tests: the oracle against dense SVD and the committed golden vectors, the C restatement against the numpy
+one, and the reference's grid-construction rules (src/compute.jl:122-145,270-279; src/utils.jl:112-141,175-191)."""
+import numpy as np
+import pytest
+
+import c_oracle as co
+import psa_oracle as po
+
+
+def test_step_size_matches_reference_table():
+    # src/compute.jl:270-279; SURVEY §8a quotes step=2 (C1), 1 (C2, C3, C5), 9 (C4: m=201 -> 4*500//201)
+    assert po.get_step_size(150, 100) == 2
+    assert po.get_step_size(1000, 103) == 1
+    assert po.get_step_size(4000, 400) == 1
+    assert po.get_step_size(201, 500) == 9
+    assert po.get_step_size(60, 100) == 12  # n < 100 branch: ly // 8
+    assert po.get_step_size(32, 4) == 1
+
+
+def test_vec2ax_readme_matrix():
+    T, eigA = po.complex_schur(po.readme_matrix(150))
+    ax = po.vec2ax(eigA)
+    assert np.allclose(ax, [-12.5, 11.0, -9.2, 11.6], atol=1e-12)  # SURVEY §8d probe
+
+
+def test_tidyaxes():
+    lo, hi = po.tidyaxes(-1.2345, 2.3456, 0.02)
+    assert lo <= -1.2345 and hi >= 2.3456 and hi - lo < 3.8
+
+
+@pytest.mark.parametrize("ax,npts", [([-1.44, 3.24, -3.8, 3.8], 20), ([-1, 2, -3, 4], 21), ([-1, 2, -4, 3], 20),
+                                      ([-2, 2, -2, 2], 15), ([-1, 1, -0.5, 3], 16)])
+def test_shift_axes_mirror_reconstructs_symmetric_grid(ax, npts):
+    """The half grid + un-mirroring (compute.jl:222-235) must give a y axis symmetric about 0 where mirrored and a Z
+    equal to evaluating f(|y|)."""
+    y, nm = po.shift_axes(ax, npts)
+    assert np.all(np.diff(y) > 0)
+    Z = np.abs(y)[:, None] * np.ones((1, 3))
+    Zf, yf = po.unmirror(Z, y, nm)
+    assert np.all(np.diff(yf) > 0)
+    assert np.allclose(Zf[:, 0], np.abs(yf))
+    assert yf[0] >= ax[2] - 1e-9 * (1 + abs(ax[2])) or nm >= 0
+    k = abs(nm)
+    assert len(yf) == len(y) + (k if nm < 0 or y[0] != 0 else min(k, len(y) - 1))
+
+
+def test_make_grid_complex_matrix_is_plain_linspace():
+    x, y, nm = po.make_grid([-1, 2, -3, 4], 17, False)
+    assert nm == 0 and len(x) == 17 and len(y) == 17 and x[0] == -1 and y[-1] == 4
+
+
+def test_oracle_matches_dense_svd_readme(golden):
+    g = golden("readme150")
+    Z, svd = g["Z"], g["svd"]
+    rel = np.abs(Z - svd) / svd
+    assert np.median(rel) < 5e-6 and rel.max() < 1e-4  # Lanczos stops at tol 1e-5 (median 5e-7, max 7e-6)
+
+
+def test_oracle_reproduces_golden(golden):
+    g = golden("readme150")
+    Z, algo, warned, it = po.psacore(g["T"], g["q0"], g["x"], g["y"], 1, want_iters=True)
+    assert algo == "sq_lanc" == str(g["algo"])
+    assert np.allclose(Z, g["Z"], rtol=1e-9) and np.array_equal(it, g["iters"])
+
+
+def test_c_oracle_matches_numpy_oracle_square(golden):
+    g = golden("readme150")
+    Zc, itc, fl = co.grid(g["T"], g["x"], g["y"], g["q0"], nthreads=4)
+    assert np.allclose(Zc, g["Z"], rtol=1e-10)
+    assert np.array_equal(itc, g["iters"]) and fl.sum() == 0
+
+
+def test_c_oracle_matches_numpy_oracle_hessqr(golden):
+    g = golden("hessqr210")
+    assert str(g["algo"]) == "HessQR"  # test/medrect.jl:16
+    Zc, itc, fl = co.grid(g["H"], g["x"], g["y"], g["q0"], nthreads=4)
+    ok = g["Z"] > 1e-13
+    assert np.allclose(Zc[ok], g["Z"][ok], rtol=1e-8)
+    assert np.mean(itc == g["iters"]) > 0.97
+
+
+def test_hessqr_drops_last_subdiagonal_entry():
+    """Reference quirk (compute.jl:581,592): the sweep never rotates H[n+1,n] in, so changing it changes nothing."""
+    H = np.asfortranarray(po.grcar(210)[:, :-1]).astype(np.complex128)
+    H2 = H.copy()
+    H2[209, 208] = 123.0
+    q0 = po.start_vector(209, 1)
+    x, y = np.array([0.5]), np.array([1.0])
+    assert po.psacore(H, q0, x, y, 2)[0][0, 0] == po.psacore(H2, q0, x, y, 2)[0][0, 0]
+
+
+def test_svd_branch_and_rect_qr_algo_symbols():
+    rng = np.random.default_rng(0)
+    T = np.triu(rng.random((32, 32)))  # test/runtests.jl:8-13 smoke case
+    Z, algo, _ = po.psacore(T, po.start_vector(32), np.linspace(0, 1, 3), np.linspace(0, 1, 3), 1)
+    assert algo == "SVD" and np.all(np.isfinite(Z))
+    A = po.grcar(190)[:, :-1]  # test/smrect.jl: m <= 200 -> rect_qr
+    Z, algo, _ = po.psacore(A, po.start_vector(189), np.array([0.5]), np.array([1.0]), 2)
+    assert algo == "rect_qr"
+
+
+def test_nonfinite_recurrence_maps_to_bigsigma():
+    """Defined behaviour where the reference has none (SURVEY §7 'Overflow'): z on an eigenvalue -> bigsigma."""
+    T = np.asfortranarray(np.triu(np.ones((60, 60), dtype=np.complex128)))
+    sig, conv, fail, it = po.psa_lanczos(T - np.eye(60), po.start_vector(60), 1e-5, 99, po.BIGSIGMA)
+    assert fail and sig == po.BIGSIGMA
+    Zc, itc, fl = co.grid(T, np.array([1.0]), np.array([0.0]), po.start_vector(60))
+    assert fl[0, 0] & 2 and Zc[0, 0] < po.PS_TINY
+
+
+def test_psa_compute_real_matrix_mirror_golden(golden):
+    g = golden("grcar120_real")
+    out = po.psa_compute(g["T"], 24, list(g["ax"]), np.diagonal(g["T"]), {"real_matrix": True},
+                         q_for_batch=lambda b, n: g["q0"])
+    ok = g["Z"] > 1e-10
+    assert np.allclose(out[0][ok], g["Z"][ok], rtol=1e-8) and np.allclose(out[2], g["y"])
+    assert np.allclose(out[2], -out[2][::-1])  # symmetric axes here: mirrored y is antisymmetric
+    assert np.allclose(out[0][ok], out[0][::-1][ok], rtol=1e-12)
+
+
+def test_recalc_levels_basic():
+    Z = np.logspace(-6, 0, 49).reshape(7, 7)
+    lev, err = po.recalc_levels(Z, [-1, 1, -1, 1])
+    assert err == 0 and len(lev) >= 2 and np.all(np.diff(lev) > 0) and lev[-1] <= np.log10(0.03 * 2) + 1e-9
+    lev, err = po.recalc_levels(np.full((3, 3), 1e-200), [-1, 1, -1, 1])
+    assert err == -2
