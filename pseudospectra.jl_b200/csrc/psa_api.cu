@@ -4,9 +4,12 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,6 +45,13 @@ struct Device {
   double2* T = nullptr;  // raw copy (m x n, ld = m)
   double2* packA = nullptr;
   double2* packB = nullptr;
+  size_t T_cap = 0, pack_cap = 0, diag_cap = 0;
+  double2* diagT = nullptr;  // eigenvalues (diagonal of T), for the scheduling-order predictor
+  // scheduling order
+  float *key_in = nullptr, *key_out = nullptr;
+  int *ord_in = nullptr, *ord_out = nullptr;
+  void* sort_tmp = nullptr;
+  size_t ord_cap = 0, sort_tmp_bytes = 0;
   // slots
   int W = 0;
   size_t vec_elems = 0;
@@ -86,7 +96,7 @@ int dev_alloc(Context* ctx, T** p, size_t count) {
 
 void free_device(Device& d) {
   cudaSetDevice(d.dev);
-  void* ptrs[] = {d.T, d.packA, d.packB, d.Q0, d.Q1, d.Wv, d.slot_point, d.slot_iter, d.slot_sel, d.slot_z,
+  void* ptrs[] = {d.diagT, d.key_in, d.key_out, d.ord_in, d.ord_out, d.sort_tmp, d.T, d.packA, d.packB, d.Q0, d.Q1, d.Wv, d.slot_point, d.slot_iter, d.slot_sel, d.slot_z,
                   d.slot_beta, d.slot_sigold, d.hist_alpha, d.hist_beta, d.active, d.fresh, d.state, d.counts,
                   d.R, d.x, d.y, d.Z, d.q0, d.iters};
   for (void* p : ptrs)
@@ -121,7 +131,7 @@ int ensure_slots(Context* ctx, Device& d, int want_W) {
   if ((rc = dev_alloc(ctx, &d.slot_sigold, W + 1))) return rc;
   if ((rc = dev_alloc(ctx, &d.hist_alpha, (size_t)(W + 1) * HIST))) return rc;
   if ((rc = dev_alloc(ctx, &d.hist_beta, (size_t)(W + 1) * HIST))) return rc;
-  if ((rc = dev_alloc(ctx, &d.active, W + 2 * NS))) return rc;
+  if ((rc = dev_alloc(ctx, &d.active, W + 2 * APAD))) return rc;
   if ((rc = dev_alloc(ctx, &d.fresh, W + 1))) return rc;
   if (hess && (rc = dev_alloc(ctx, &d.R, (size_t)(W + 1) * r_elems))) return rc;
   // scratch slot W: benign, finite contents
@@ -162,8 +172,14 @@ int set_solve_attr(Context* ctx) {
   if (ctx->solve_attr_set) return PSA_OK;
   for (auto& d : ctx->devs) {
     PSA_CUDA(cudaSetDevice(d.dev));
-    PSA_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_SMEM));
-    PSA_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    PSA_CUDA(cudaFuncSetAttribute(solve_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem(64)));
+    PSA_CUDA(cudaFuncSetAttribute(solve_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem(48)));
+    PSA_CUDA(cudaFuncSetAttribute(solve_kernel<48>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    PSA_CUDA(cudaFuncSetAttribute(solve_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem(32)));
+    PSA_CUDA(cudaFuncSetAttribute(solve_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem(16)));
+    PSA_CUDA(cudaFuncSetAttribute(solve_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    PSA_CUDA(cudaFuncSetAttribute(solve_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    PSA_CUDA(cudaFuncSetAttribute(solve_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int rc = hess_set_attrs();
     if (rc != 0) {
       ctx->err = "cudaFuncSetAttribute failed for the HessQR kernels";
@@ -191,18 +207,50 @@ SolveParams solve_params(const Context* ctx, const Device& d) {
   return sp;
 }
 
+// Panel width for a tick: the narrowest panel width (a multiple of 16 up to 64) for which all panels are
+// co-resident (2 CTAs per SM).  Wide panels reuse each T tile for more shifts; narrower ones spread the active
+// shifts evenly over every SM when fewer than 2*SMs*64 are active (grid tails, strong scaling over many GPUs).
+int pick_panel_width(int n_active, int num_sms) {
+  const char* env = getenv("PSA_PANEL_WIDTH");  // experiments only
+  const int forced = env ? atoi(env) : 0;
+  if (forced == 64 || forced == 48 || forced == 32 || forced == 16) return forced;
+  const int slots = 2 * num_sms;
+  for (int w = 16; w < 64; w += 16)
+    if ((n_active + w - 1) / w <= slots) return w;
+  return 64;
+}
+
+void launch_solve(const Context* ctx, const Device& d, int n_active, int width) {
+  const SolveParams sp = solve_params(ctx, d);
+  const int panels = (n_active + width - 1) / width;
+  switch (width) {
+    case 64: solve_kernel<64><<<panels, SOLVE_THREADS, solve_smem(64), d.stream>>>(sp); break;
+    case 48: solve_kernel<48><<<panels, SOLVE_THREADS, solve_smem(48), d.stream>>>(sp); break;
+    case 32: solve_kernel<32><<<panels, SOLVE_THREADS, solve_smem(32), d.stream>>>(sp); break;
+    default: solve_kernel<16><<<panels, SOLVE_THREADS, solve_smem(16), d.stream>>>(sp); break;
+  }
+}
+
 // pack / prepare the device-resident matrix on one device (d.T already holds the raw m x n copy)
 int prepare_matrix(Context* ctx, Device& d) {
   PSA_CUDA(cudaSetDevice(d.dev));
   if (ctx->algo == PSA_ALGO_SQ_LANC) {
     const long long ntiles = tiles_per_phase(ctx->nblk);
     int rc;
-    if ((rc = dev_alloc(ctx, &d.packA, (size_t)ntiles * TILE_ELEMS))) return rc;
-    if ((rc = dev_alloc(ctx, &d.packB, (size_t)ntiles * TILE_ELEMS))) return rc;
+    if (d.pack_cap < (size_t)ntiles * TILE_ELEMS) {  // buffers are reused across set_matrix calls of the same size
+      if ((rc = dev_alloc(ctx, &d.packA, (size_t)ntiles * TILE_ELEMS))) return rc;
+      if ((rc = dev_alloc(ctx, &d.packB, (size_t)ntiles * TILE_ELEMS))) return rc;
+      d.pack_cap = (size_t)ntiles * TILE_ELEMS;
+    }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     cudaEventRecord(e0, d.stream);
+    if (d.diag_cap < (size_t)ctx->n) {
+      if ((rc = dev_alloc(ctx, &d.diagT, (size_t)ctx->n))) return rc;
+      d.diag_cap = (size_t)ctx->n;
+    }
+    diag_kernel<<<(ctx->n + 255) / 256, 256, 0, d.stream>>>(d.T, ctx->m, ctx->n, d.diagT);
     const int grid = (int)std::min<long long>(2 * ntiles, 148LL * 32);
     pack_kernel<<<grid, 256, 0, d.stream>>>(d.T, ctx->m, ctx->n, ctx->n_pad, ctx->nblk, d.packA, d.packB);
     cudaEventRecord(e1, d.stream);
@@ -213,12 +261,8 @@ int prepare_matrix(Context* ctx, Device& d) {
     if (&d == &ctx->devs[0]) ctx->stats[PSA_STAT_PACK_MS] = ms;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    // the raw copy is no longer needed on the square path
-    cudaFree(d.T);
-    d.T = nullptr;
   }
-  d.W = 0;  // slot buffers depend on n_pad / algo: force re-allocation
-  return PSA_OK;
+  return PSA_OK;  // slot buffers are re-validated by ensure_slots (they depend on n_pad / algo)
 }
 
 int classify(int m, int n) {
@@ -242,6 +286,7 @@ int run_grid(Context* ctx, const GridArgs& g, std::vector<double*>& Zout, std::v
   int rc = set_solve_attr(ctx);
   if (rc) return rc;
   std::vector<int> rows(ng), P(ng), done(ng, 0);
+  std::vector<const int*> order(ng, nullptr);
   std::vector<size_t> nev(ng, 0);
   double launches = 0, solve_launches = 0, ticks = 0;
   for (int i = 0; i < ng; ++i) {
@@ -255,6 +300,32 @@ int run_grid(Context* ctx, const GridArgs& g, std::vector<double*>& Zout, std::v
     PSA_CUDA(cudaMemsetAsync(d.counts, 0, PSA_NCOUNTS * sizeof(unsigned long long), d.stream));
     PSA_CUDA(cudaEventRecord(d.g0, d.stream));
     if (P[i] == 0) done[i] = 1;
+    order[i] = nullptr;
+    if (ctx->algo == PSA_ALGO_SQ_LANC && P[i] > d.W && !getenv("PSA_NATURAL_ORDER")) {
+      // more points than slots: queue them longest-job-first (see predict_kernel)
+      if (d.ord_cap < (size_t)P[i]) {
+        if ((rc = dev_alloc(ctx, &d.key_in, (size_t)P[i]))) return rc;
+        if ((rc = dev_alloc(ctx, &d.key_out, (size_t)P[i]))) return rc;
+        if ((rc = dev_alloc(ctx, &d.ord_in, (size_t)P[i]))) return rc;
+        if ((rc = dev_alloc(ctx, &d.ord_out, (size_t)P[i]))) return rc;
+        d.ord_cap = (size_t)P[i];
+      }
+      predict_kernel<<<(P[i] + 255) / 256, 256, 0, d.stream>>>(P[i], rows[i], i, ng, d.x, d.y, d.diagT, ctx->n, d.key_in,
+                                                               d.ord_in);
+      size_t need = 0;
+      cub::DeviceRadixSort::SortPairsDescending(nullptr, need, d.key_in, d.key_out, d.ord_in, d.ord_out, P[i], 0, 32,
+                                                d.stream);
+      if (need > d.sort_tmp_bytes) {
+        if (d.sort_tmp) cudaFree(d.sort_tmp);
+        d.sort_tmp = nullptr;
+        PSA_CUDA(cudaMalloc(&d.sort_tmp, need));
+        d.sort_tmp_bytes = need;
+      }
+      PSA_CUDA(cub::DeviceRadixSort::SortPairsDescending(d.sort_tmp, need, d.key_in, d.key_out, d.ord_in, d.ord_out, P[i],
+                                                         0, 32, d.stream));
+      order[i] = d.ord_out;
+      launches += 2;
+    }
   }
   const int hist_maxit = std::min(g.maxit, HIST - 2);
   int remaining = 0;
@@ -278,6 +349,7 @@ int run_grid(Context* ctx, const GridArgs& g, std::vector<double*>& Zout, std::v
       sp.row_step = ng;
       sp.x = d.x;
       sp.y = d.y;
+      sp.order = order[i];
       sp.slot_point = d.slot_point;
       sp.slot_z = d.slot_z;
       sp.slot_iter = d.slot_iter;
@@ -310,9 +382,8 @@ int run_grid(Context* ctx, const GridArgs& g, std::vector<double*>& Zout, std::v
           init_fresh_kernel<<<n_fresh, 256, 0, d.stream>>>(d.fresh, ctx->n_pad, ctx->n, d.q0, d.Q0);
           launches += 1;
         }
-        const int panels = (n_active + NS - 1) / NS;
         PSA_CUDA(cudaEventRecord(ep.a, d.stream));
-        solve_kernel<<<panels, SOLVE_THREADS, SOLVE_SMEM, d.stream>>>(solve_params(ctx, d));
+        launch_solve(ctx, d, n_active, pick_panel_width(n_active, d.num_sms));
         PSA_CUDA(cudaEventRecord(ep.b, d.stream));
         launches += 1;
         solve_launches += (i == 0);
@@ -496,14 +567,20 @@ static int set_matrix_common(Context* ctx, const double* T, int64_t ldt, int m, 
   Device& d0 = ctx->devs[0];
   PSA_CUDA(cudaSetDevice(d0.dev));
   int rc;
-  if ((rc = dev_alloc(ctx, &d0.T, (size_t)m * n))) return rc;
+  if (d0.T_cap < (size_t)m * n) {
+    if ((rc = dev_alloc(ctx, &d0.T, (size_t)m * n))) return rc;
+    d0.T_cap = (size_t)m * n;
+  }
   PSA_CUDA(cudaMemcpy2DAsync(d0.T, (size_t)m * 16, T, (size_t)ldt * 16, (size_t)m * 16, n,
                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, d0.stream));
   PSA_CUDA(cudaStreamSynchronize(d0.stream));
   for (size_t i = 1; i < ctx->devs.size(); ++i) {
     Device& d = ctx->devs[i];
     PSA_CUDA(cudaSetDevice(d.dev));
-    if ((rc = dev_alloc(ctx, &d.T, (size_t)m * n))) return rc;
+    if (d.T_cap < (size_t)m * n) {
+      if ((rc = dev_alloc(ctx, &d.T, (size_t)m * n))) return rc;
+      d.T_cap = (size_t)m * n;
+    }
     PSA_CUDA(cudaMemcpyPeerAsync(d.T, d.dev, d0.T, d0.dev, (size_t)m * n * 16, d.stream));
   }
   ctx->algo = algo;
@@ -619,7 +696,7 @@ int psa_gpu_apply_resolvent(void* vctx, const double* z, int ns, const double* Q
   PSA_CUDA(cudaSetDevice(d.dev));
   int rc = set_solve_attr(ctx);
   if (rc) return rc;
-  const int W = (ns + NS - 1) / NS * NS;
+  const int W = (ns + APAD - 1) / APAD * APAD;  // padded active list
   if ((rc = ensure_slots(ctx, d, std::max(W, d.W)))) return rc;
   double2 *dQ = nullptr, *dz = nullptr, *dV = nullptr;
   const size_t n = ctx->n;
@@ -630,11 +707,21 @@ int psa_gpu_apply_resolvent(void* vctx, const double* z, int ns, const double* Q
   PSA_CUDA(cudaMemcpyAsync(dz, z, (size_t)ns * 16, cudaMemcpyHostToDevice, d.stream));
   load_slots_kernel<<<W, 256, 0, d.stream>>>(ns, ctx->n, ctx->n_pad, dQ, dz, d.Q0, d.slot_z, d.slot_sel, d.active, d.W,
                                              d.state);
-  solve_kernel<<<W / NS, SOLVE_THREADS, SOLVE_SMEM, d.stream>>>(solve_params(ctx, d));
+  EventPair& ep = event_pair(d, 0);
+  PSA_CUDA(cudaEventRecord(ep.a, d.stream));
+  launch_solve(ctx, d, ns, pick_panel_width(ns, d.num_sms));
+  PSA_CUDA(cudaEventRecord(ep.b, d.stream));
   store_slots_kernel<<<ns, 256, 0, d.stream>>>(ctx->n, ctx->n_pad, d.Wv, dV);
   PSA_CUDA(cudaGetLastError());
   PSA_CUDA(cudaMemcpyAsync(V, dV, ns * n * 16, cudaMemcpyDeviceToHost, d.stream));
   PSA_CUDA(cudaStreamSynchronize(d.stream));
+  {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ep.a, ep.b);
+    ctx->stats[PSA_STAT_SOLVE_MS] = ms;
+    ctx->stats[PSA_STAT_SOLVE_LAUNCHES] = 1;
+    ctx->stats[PSA_STAT_FLOPS] = 8.0 * (double)n * (double)n * ns;
+  }
   cudaFree(dQ);
   cudaFree(dz);
   cudaFree(dV);

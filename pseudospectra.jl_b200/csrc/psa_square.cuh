@@ -13,17 +13,18 @@ namespace psa {
 // ---- tiling constants -------------------------------------------------------------------------------
 constexpr int MB = 64;                        // rows per block row (M tile)
 constexpr int KC = 16;                        // contraction chunk (one pipeline step)
-constexpr int NS = 64;                        // shifts per panel (N tile) = one CTA
+constexpr int NS = 64;                        // widest panel (shifts per CTA)
+constexpr int APAD = 192;                     // active lists are padded to a multiple of lcm(16,32,48,64)
 constexpr int CPB = MB / KC;                  // chunks per block = 4
 constexpr int TILE_ELEMS = MB * KC;           // complex elements per packed T tile
 constexpr int TILE_BYTES = TILE_ELEMS * 16;   // 16 KiB
 constexpr int XROW_BYTES = KC * 16 + 64;      // 320: X smem row stride (64 B pad -> conflict-free B-fragment loads)
-constexpr int XT_BYTES = NS * XROW_BYTES;     // 20 KiB
-constexpr int STAGE_BYTES = TILE_BYTES + XT_BYTES;
 constexpr int STAGES = 3;                     // <= 4 (producer/consumer distance rule)
 constexpr int SOLVE_THREADS = 256;
-constexpr int SOLVE_SMEM_AUX = 32 + NS * 16 + NS * 8 * 2;  // mbarriers (padded) + shifts + 2 pointer tables
-constexpr int SOLVE_SMEM = STAGES * STAGE_BYTES + SOLVE_SMEM_AUX;
+// per panel width NSV (64, 32 or 16 shifts per CTA): X tile NSV rows, ring of STAGES (T tile + X tile) stages,
+// then mbarriers (32 B reserved) + shifts + 2 pointer tables
+__host__ __device__ constexpr int stage_bytes(int nsv) { return TILE_BYTES + nsv * XROW_BYTES; }
+__host__ __device__ constexpr int solve_smem(int nsv) { return STAGES * stage_bytes(nsv) + 32 + nsv * 16 + nsv * 8 * 2; }
 static_assert(STAGES * 8 <= 32, "mbarrier block");
 constexpr int HIST = 128;                     // per-slot alpha/beta history stride (maxit <= 126)
 
@@ -78,6 +79,43 @@ __global__ void pack_kernel(const double2* __restrict__ T, long long ldt, int n,
   }
 }
 
+__global__ void diag_kernel(const double2* __restrict__ T, long long ldt, int n, double2* __restrict__ diag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) diag[i] = T[(long long)i * ldt + i];
+}
+
+// Cost predictor for longest-job-first scheduling: inverse Lanczos converges fast where the resolvent norm is
+// large (near the spectrum) and slowly far from it, so points are queued by decreasing distance to the nearest
+// eigenvalue (diag T).  Only the ORDER of the work changes; every point's result is independent of it.
+__global__ void __launch_bounds__(256) predict_kernel(int P, int rows_local, int row0, int row_step,
+                                                       const double* __restrict__ x, const double* __restrict__ y,
+                                                       const double2* __restrict__ diag, int n,
+                                                       float* __restrict__ key, int* __restrict__ val) {
+  __shared__ double2 ev[256];
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  double zx = 0.0, zy = 0.0;
+  if (p < P) {
+    const int jr = p % rows_local, k = p / rows_local;
+    zx = x[k];
+    zy = y[row0 + jr * row_step];
+  }
+  double best = 1e300;
+  for (int base = 0; base < n; base += 256) {
+    __syncthreads();
+    if (base + threadIdx.x < n) ev[threadIdx.x] = diag[base + threadIdx.x];
+    __syncthreads();
+    const int cnt = min(256, n - base);
+    for (int i = 0; i < cnt; ++i) {
+      const double dx = ev[i].x - zx, dy = ev[i].y - zy;
+      best = fmin(best, dx * dx + dy * dy);
+    }
+  }
+  if (p < P) {
+    key[p] = (float)best;
+    val[p] = p;
+  }
+}
+
 // ---- the solve kernel ---------------------------------------------------------------------------------
 struct SolveParams {
   const double2* packA;
@@ -102,27 +140,32 @@ struct StepCursor {
   }
 };
 
-// One CTA = one panel of NS shifts; 8 warps arranged 4 (M) x 2 (N): warp tile 16 rows x 32 shifts.
+// One CTA = one panel of NSV shifts (64 in steady state; 32 / 16 when few shifts are active, so that the
+// panels still cover every SM); 8 warps arranged 4 (M) x 2 (N): warp tile 16 rows x NSV/2 shifts.
 // Left-looking block forward substitution (both phases, see pack_kernel): for block row I
 //   acc = sum_{c < 4I} L[I][c] * X[c]              (GEMM steps: T tile + X tile through the bulk-copy ring)
 //   for cp = 0..3: rows 16cp..16cp+15:  x = (L_dd - z)^{-1} (rhs - acc)   (diag step, per-shift, in registers)
 //                  acc += L[I][4I+cp] * x           (rows below, same DMMA code)
+template <int NSV>
 __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_kernel(SolveParams P) {
+  constexpr int SW = NSV / 2;  // shifts per warp
+  constexpr int NT = SW / 8;   // 8-wide DMMA column tiles per warp
+  constexpr int STAGE_BYTES = stage_bytes(NSV);
   extern __shared__ __align__(128) unsigned char smem[];
   const int n_active = *P.n_active;
   const int panel = blockIdx.x;
-  if (panel * NS >= n_active) return;
+  if (panel * NSV >= n_active) return;
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // 32 B reserved
   double2* zsh = reinterpret_cast<double2*>(smem + STAGES * STAGE_BYTES + 32);    // 16 B aligned
-  double2** wptr = reinterpret_cast<double2**>(zsh + NS);
-  const double2** qptr = (const double2**)(wptr + NS);
+  double2** wptr = reinterpret_cast<double2**>(zsh + NSV);
+  const double2** qptr = (const double2**)(wptr + NSV);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp & 3, wn = warp >> 2;
 
-  if (tid < NS) {
-    const int slot = P.active[panel * NS + tid];
+  if (tid < NSV) {
+    const int slot = P.active[panel * NSV + tid];
     wptr[tid] = P.Wv + (size_t)slot * P.n_pad;
     qptr[tid] = (P.sel[slot] ? P.Q1 : P.Q0) + (size_t)slot * P.n_pad;
     zsh[tid] = P.z[slot];
@@ -142,7 +185,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_kernel(SolveParams P) 
   auto issue = [&](const StepCursor& pc, int stage) {
     unsigned char* sb = smem + stage * STAGE_BYTES;
     const bool needX = pc.c < CPB * pc.I;
-    if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], TILE_BYTES + (needX ? NS * KC * 16 : 0));
+    if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], TILE_BYTES + (needX ? NSV * KC * 16 : 0));
     __syncwarp();
     if (lane == 0) {
       const double2* src = (pc.phase ? P.packB : P.packA) + tile_index(pc.I, pc.c) * TILE_ELEMS;
@@ -151,46 +194,46 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_kernel(SolveParams P) 
     if (needX) {
       const int mem0 = pc.phase ? n_pad - KC * pc.c - KC : KC * pc.c;
 #pragma unroll
-      for (int s = lane; s < NS; s += 32)
+      for (int s = lane; s < NSV; s += 32)
         bulk_g2s(sb + TILE_BYTES + s * XROW_BYTES, wptr[s] + mem0, KC * 16, &full_bar[stage]);
     }
   };
 
-  double cre[2][4][2], cim[2][4][2];
+  double cre[2][NT][2], cim[2][NT][2];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) cre[a][b][0] = cre[a][b][1] = cim[a][b][0] = cim[a][b][1] = 0.0;
+    for (int b = 0; b < NT; ++b) cre[a][b][0] = cre[a][b][1] = cim[a][b][0] = cim[a][b][1] = 0.0;
 
   auto gemm_step = [&](const unsigned char* sb, int flip) {
     const double2* At = reinterpret_cast<const double2*>(sb);
-    const unsigned char* Xt = sb + TILE_BYTES + (32 * wn + (lane >> 2)) * XROW_BYTES;
+    const unsigned char* Xt = sb + TILE_BYTES + (SW * wn + (lane >> 2)) * XROW_BYTES;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      double2 a[2], b[4];
+      double2 a[2], b[NT];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) a[mt] = At[(j * 8 + 2 * wm + mt) * 32 + lane];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
+      for (int nt = 0; nt < NT; ++nt)
         b[nt] = *reinterpret_cast<const double2*>(Xt + nt * 8 * XROW_BYTES + (((4 * j + (lane & 3)) ^ flip) << 4));
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) dmma884(cre[mt][nt][0], cre[mt][nt][1], a[mt].x, b[nt].x);
+        for (int nt = 0; nt < NT; ++nt) dmma884(cre[mt][nt][0], cre[mt][nt][1], a[mt].x, b[nt].x);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) dmma884(cim[mt][nt][0], cim[mt][nt][1], a[mt].x, b[nt].y);
+        for (int nt = 0; nt < NT; ++nt) dmma884(cim[mt][nt][0], cim[mt][nt][1], a[mt].x, b[nt].y);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         const double nai = -a[mt].y;
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) dmma884(cre[mt][nt][0], cre[mt][nt][1], nai, b[nt].y);
+        for (int nt = 0; nt < NT; ++nt) dmma884(cre[mt][nt][0], cre[mt][nt][1], nai, b[nt].y);
       }
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) dmma884(cim[mt][nt][0], cim[mt][nt][1], a[mt].y, b[nt].x);
+        for (int nt = 0; nt < NT; ++nt) dmma884(cim[mt][nt][0], cim[mt][nt][1], a[mt].y, b[nt].x);
     }
   };
 
@@ -218,8 +261,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_kernel(SolveParams P) 
     } else {
       const int cp = cons.c - CPB * cons.I;  // diagonal sub-chunk 0..3
       if (wm == cp) {
-        // this warp owns rows 16cp..16cp+15 of the block row for its 32 shifts: finish them.
-        const int s = 32 * wn + lane;
+        // this warp owns rows 16cp..16cp+15 of the block row for its SW shifts: finish them (lane = shift).
+        const bool solver = lane < SW;
+        const int s = SW * wn + (solver ? lane : 0);
         const int mem0 = cons.phase ? n_pad - KC * cons.c - KC : KC * cons.c;
         const double2* rp = (cons.phase ? (const double2*)wptr[s] : qptr[s]) + mem0;
         double2 b[KC];  // indexed by processing row r; memory / smem position is r ^ flip
@@ -230,10 +274,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_kernel(SolveParams P) 
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt)
+          for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int r = 8 * mt + (lane >> 2), sl = 32 * wn + 8 * nt + 2 * (lane & 3) + e;
+              const int r = 8 * mt + (lane >> 2), sl = SW * wn + 8 * nt + 2 * (lane & 3) + e;
               *reinterpret_cast<double2*>(Xt + sl * XROW_BYTES + ((r ^ flip) << 4)) =
                   make_double2(cre[mt][nt][e], cim[mt][nt][e]);
               cre[mt][nt][e] = 0.0;
@@ -269,10 +313,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_kernel(SolveParams P) 
           }
         }
         double2* op_ = wptr[s] + mem0;
+        if (solver) {
 #pragma unroll
-        for (int r = 0; r < KC; ++r) {
-          xrow[r ^ flip] = b[r];
-          op_[r ^ flip] = b[r];
+          for (int r = 0; r < KC; ++r) {
+            xrow[r ^ flip] = b[r];
+            op_[r ^ flip] = b[r];
+          }
         }
         fence_proxy_async();  // the next block rows read these x through the async proxy
       }
@@ -297,6 +343,7 @@ struct SchedParams {
   int row0, row_step; // global row of local row r: row0 + r*row_step
   const double* x;    // lx
   const double* y;    // ly (global)
+  const int* order;   // nullable: queue position -> local point index (longest-job-first order)
   int* slot_point;    // local point index or -1
   double2* slot_z;
   int* slot_iter;
@@ -338,8 +385,9 @@ __global__ void __launch_bounds__(1024) sched_kernel(SchedParams S) {
   const int n_fresh = max(0, min(total_idle, S.P - head));
   for (int i = lo; i < hi; ++i) {
     if (S.slot_point[i] < 0) {
-      const int p = head + rank;
-      if (p < S.P) {
+      const int qpos = head + rank;
+      if (qpos < S.P) {
+        const int p = S.order ? S.order[qpos] : qpos;
         const int jr = p % S.rows_local, k = p / S.rows_local;
         const int j = S.row0 + jr * S.row_step;
         S.slot_point[i] = p;
@@ -359,7 +407,7 @@ __global__ void __launch_bounds__(1024) sched_kernel(SchedParams S) {
   const int n_active = base_s;
   for (int i = lo; i < hi; ++i)
     if (S.slot_point[i] >= 0) S.active[arank++] = i;
-  const int padded = (n_active + NS - 1) / NS * NS;
+  const int padded = (n_active + APAD - 1) / APAD * APAD;
   for (int i = n_active + tid; i < padded; i += 1024) S.active[i] = S.W;
   if (tid == 0) {
     S.state[0] = head + n_fresh;
@@ -456,7 +504,6 @@ constexpr int LZ_THREADS = 256;
 __global__ void __launch_bounds__(LZ_THREADS) lanczos_kernel(LanczosParams L) {
   __shared__ double red[LZ_THREADS / 32];
   __shared__ double sd[HIST], se2[HIST];
-  __shared__ double s_sigma;
   if ((int)blockIdx.x >= *L.n_active) return;
   const int slot = L.active[blockIdx.x];
   const int tid = threadIdx.x;
