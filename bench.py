@@ -47,7 +47,12 @@ def build_workload(n: int, npts: int, seed: int = 1):
     else:
         rng = np.random.default_rng(seed)
         A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
-        T, _ = sla.schur(A, output="complex")
+        try:  # torchrun exports OMP_NUM_THREADS=1; the one-time host reduction should use the host's cores
+            from threadpoolctl import threadpool_limits
+            with threadpool_limits(limits=os.cpu_count()):
+                T, _ = sla.schur(A, output="complex")
+        except ImportError:
+            T, _ = sla.schur(A, output="complex")
         T = np.triu(T)
         try:
             os.makedirs(os.path.dirname(cache), exist_ok=True)
@@ -177,7 +182,7 @@ def run_reference(args):
            "config": workload_config(args, ax), "cpu_baseline": last,
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "schur_s": schur_s, "schur": how}
-    print(json.dumps(out), flush=True)
+    emit(out)
     return 0
 
 
@@ -348,7 +353,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             cb, _, _ = cpu_arm(T_np, x, y, q0, args.cpu_seconds, os.cpu_count() or 1)
             out["cpu_baseline"] = cb
-        print(json.dumps(out), flush=True)
+        emit(out)
     ctx.close()
     if world > 1:
         dist.barrier()
@@ -356,7 +361,20 @@ def run_ours(args):
     return 0
 
 
+def emit(obj):
+    """Print the one JSON line on the real stdout (libraries such as NCCL may write to fd 1, which main() has
+    pointed at stderr)."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # anything else that prints to stdout goes to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
