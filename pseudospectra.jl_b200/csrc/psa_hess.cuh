@@ -14,9 +14,13 @@ constexpr int HS_THREADS = 256;  // solve kernel
 constexpr int HB = 32;           // diagonal block of the per-shift triangular solves
 
 inline size_t hess_R_elems(int n) { return (size_t)n * n; }  // column-major n x n per slot, ld = n
+// Slots in flight: enough CTAs to keep HBM busy and to amortise the per-tick launches, bounded by a 24 GB budget
+// for the private triangular factors.
 inline long long hess_slot_capacity(int n, int num_sms) {
-  (void)n;
-  return 4LL * num_sms;
+  const long long by_mem = (24LL << 30) / ((long long)hess_R_elems(n) * 16 + 1);
+  long long w = 64LL * num_sms;
+  if (w > by_mem) w = by_mem;
+  return w < 64 ? 64 : w / 64 * 64;
 }
 
 // zlartg-convention Givens (Julia `givens(f,g,1,2)`, compute.jl:585): [c s; -conj(s) c][f; g] = [r; 0], c real
