@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpsagpu.so")
+LIB_PATH = os.environ.get("PSA_LIB_PATH") or os.path.join(_HERE, "libpsagpu.so")  # env override: experiments only
 
 PSA_OK = 0
 PSA_ERR_ARG, PSA_ERR_CUDA, PSA_ERR_CANCELLED, PSA_ERR_UNSUPPORTED = -1, -2, -3, -4

@@ -207,17 +207,28 @@ SolveParams solve_params(const Context* ctx, const Device& d) {
   return sp;
 }
 
-// Panel width for a tick: the narrowest panel width (a multiple of 16 up to 64) for which all panels are
-// co-resident (2 CTAs per SM).  Wide panels reuse each T tile for more shifts; narrower ones spread the active
-// shifts evenly over every SM when fewer than 2*SMs*64 are active (grid tails, strong scaling over many GPUs).
+// Panel width for a tick.  Wide panels reuse each T tile for more shifts; narrow ones spread the active shifts
+// over every SM when few are active (grid tails, strong scaling over many GPUs).  The choice minimises a small
+// cost model measured on B200 (profiles/r01_panel_sweep.txt): launch time, relative to a full 64-wide launch,
+// of a CTA running alone on its SM (T1) and of two co-resident CTAs (T2); more panels than 2 per SM run in rounds.
 int pick_panel_width(int n_active, int num_sms) {
   const char* env = getenv("PSA_PANEL_WIDTH");  // experiments only
   const int forced = env ? atoi(env) : 0;
   if (forced == 64 || forced == 48 || forced == 32 || forced == 16) return forced;
-  const int slots = 2 * num_sms;
-  for (int w = 16; w < 64; w += 16)
-    if ((n_active + w - 1) / w <= slots) return w;
-  return 64;
+  static const int widths[4] = {16, 32, 48, 64};
+  static const double t1[4] = {0.209, 0.331, 0.453, 0.584}, t2[4] = {0.309, 0.538, 0.775, 1.0};
+  int best = 64;
+  double best_cost = 1e300;
+  for (int i = 0; i < 4; ++i) {
+    const int panels = (n_active + widths[i] - 1) / widths[i];
+    const int per_sm = (panels + num_sms - 1) / num_sms;  // CTAs on the busiest SM
+    const double cost = (per_sm / 2) * t2[i] + (per_sm % 2) * t1[i];
+    if (cost < best_cost - 1e-12) {
+      best_cost = cost;
+      best = widths[i];
+    }
+  }
+  return best;
 }
 
 void launch_solve(const Context* ctx, const Device& d, int n_active, int width) {

@@ -14,7 +14,7 @@ namespace psa {
 constexpr int MB = 64;                        // rows per block row (M tile)
 constexpr int KC = 16;                        // contraction chunk (one pipeline step)
 constexpr int NS = 64;                        // widest panel (shifts per CTA)
-constexpr int APAD = 192;                     // active lists are padded to a multiple of lcm(16,32,48,64)
+constexpr int APAD = 384;                     // active lists are padded to a multiple of lcm(16,32,48,64,96,128)
 constexpr int CPB = MB / KC;                  // chunks per block = 4
 constexpr int TILE_ELEMS = MB * KC;           // complex elements per packed T tile
 constexpr int TILE_BYTES = TILE_ELEMS * 16;   // 16 KiB
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_kernel(SolveParams P) 
   const double2** qptr = (const double2**)(wptr + NSV);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wm = warp & 3, wn = warp >> 2;
+  const int wm = warp >> 1, wn = warp & 1;  // the 2 warps sharing a row group sit on different SM sub-partitions
 
   if (tid < NSV) {
     const int slot = P.active[panel * NSV + tid];
@@ -181,21 +181,22 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_kernel(SolveParams P) 
   const int steps_per_phase = (int)tiles_per_phase(nblk);
   const int total_steps = 2 * steps_per_phase;
 
-  // producer side: issue the loads of one step into its ring stage (called by warp 0 only)
+  // producer side: issue the loads of one step into its ring stage.  Called by ALL warps: a bulk copy is a
+  // uniform-datapath instruction (UBLKCP), so per-lane copies are serialised inside a warp; spreading the NSV row
+  // copies over the 8 warps keeps that serial issue off any single warp's critical path.
   auto issue = [&](const StepCursor& pc, int stage) {
+    constexpr int RPW = NSV / (SOLVE_THREADS / 32);  // X rows issued per warp
     unsigned char* sb = smem + stage * STAGE_BYTES;
     const bool needX = pc.c < CPB * pc.I;
-    if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], TILE_BYTES + (needX ? NSV * KC * 16 : 0));
-    __syncwarp();
-    if (lane == 0) {
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&full_bar[stage], TILE_BYTES + (needX ? NSV * KC * 16 : 0));
       const double2* src = (pc.phase ? P.packB : P.packA) + tile_index(pc.I, pc.c) * TILE_ELEMS;
       bulk_g2s(sb, src, TILE_BYTES, &full_bar[stage]);
     }
-    if (needX) {
+    if (needX && lane < RPW) {
       const int mem0 = pc.phase ? n_pad - KC * pc.c - KC : KC * pc.c;
-#pragma unroll
-      for (int s = lane; s < NSV; s += 32)
-        bulk_g2s(sb + TILE_BYTES + s * XROW_BYTES, wptr[s] + mem0, KC * 16, &full_bar[stage]);
+      const int s = warp * RPW + lane;
+      bulk_g2s(sb + TILE_BYTES + s * XROW_BYTES, wptr[s] + mem0, KC * 16, &full_bar[stage]);
     }
   };
 
@@ -242,11 +243,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_kernel(SolveParams P) 
     prod.advance();
     if (prod.I == nblk) prod = StepCursor{1, 0, 0};
   };
-  if (warp == 0) {
-    for (int s = 0; s < STAGES && s < total_steps; ++s) {
-      issue(prod, s);
-      advance_prod();
-    }
+  for (int s = 0; s < STAGES && s < total_steps; ++s) {
+    issue(prod, s);
+    advance_prod();
   }
 
   for (int t = 0; t < total_steps; ++t) {
@@ -326,7 +325,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_kernel(SolveParams P) 
       if (wm > cp) gemm_step(sb, flip);
     }
     __syncthreads();  // every warp is done with this stage: refill it
-    if (warp == 0 && t + STAGES < total_steps) {
+    if (t + STAGES < total_steps) {
       issue(prod, stage);
       advance_prod();
     }
