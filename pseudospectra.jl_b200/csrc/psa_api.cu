@@ -16,6 +16,7 @@
 
 #include "../../include/psa_gpu.h"
 #include "psa_hess.cuh"
+#include "psa_nccl.h"
 #include "psa_square.cuh"
 
 namespace {
@@ -31,6 +32,15 @@ using namespace psa;
       ctx->err = buf_;                                                                         \
       return e_ == cudaErrorMemoryAllocation ? PSA_ERR_NOMEM : PSA_ERR_CUDA;                   \
     }                                                                                          \
+  } while (0)
+
+#define PSA_NCCL(call)                                                                               \
+  do {                                                                                               \
+    ncclResult_t r_ = (call);                                                                        \
+    if (r_ != ncclSuccess) {                                                                         \
+      ctx->err = std::string(#call) + " failed: " + ctx->nccl.GetErrorString(r_);                    \
+      return PSA_ERR_NCCL;                                                                           \
+    }                                                                                                \
   } while (0)
 
 struct EventPair {
@@ -79,10 +89,38 @@ struct Device {
 struct Context {
   std::vector<Device> devs;
   std::string err;
+  NcclApi nccl;                    // multi-device contexts only
+  std::vector<ncclComm_t> comms;   // one communicator per device (ncclCommInitAll)
+  std::vector<double*> gather_buf; // on device 0: receive buffers for the other devices' tiles
+  std::vector<int*> gather_ibuf;
+  std::vector<size_t> gather_cap;
   int m = 0, n = 0, n_pad = 0, nblk = 0, algo = PSA_ALGO_NONE;
   double stats[PSA_NSTATS] = {0};
   bool solve_attr_set = false;
 };
+
+template <typename T>
+int dev_alloc(Context* ctx, T** p, size_t count);
+
+// Communicators over the context's devices (created lazily: single-device contexts never touch NCCL).
+int ensure_comms(Context* ctx) {
+  if (!ctx->comms.empty()) return PSA_OK;
+  if (!ctx->nccl.load(ctx->err)) return PSA_ERR_NCCL;
+  const int ng = (int)ctx->devs.size();
+  std::vector<int> ids(ng);
+  for (int i = 0; i < ng; ++i) ids[i] = ctx->devs[i].dev;
+  ctx->comms.assign(ng, nullptr);
+  ncclResult_t r = ctx->nccl.CommInitAll(ctx->comms.data(), ng, ids.data());
+  if (r != ncclSuccess) {
+    ctx->err = std::string("ncclCommInitAll failed: ") + ctx->nccl.GetErrorString(r);
+    ctx->comms.clear();
+    return PSA_ERR_NCCL;
+  }
+  ctx->gather_buf.assign(ng, nullptr);
+  ctx->gather_ibuf.assign(ng, nullptr);
+  ctx->gather_cap.assign(ng, 0);
+  return PSA_OK;
+}
 
 template <typename T>
 int dev_alloc(Context* ctx, T** p, size_t count) {
@@ -560,6 +598,13 @@ int psa_gpu_init(int ngpus, const int* device_ids, void** out) {
 int psa_gpu_free(void* vctx) {
   if (!vctx) return PSA_ERR_ARG;
   Context* ctx = static_cast<Context*>(vctx);
+  if (!ctx->devs.empty()) cudaSetDevice(ctx->devs[0].dev);
+  for (double* p : ctx->gather_buf)
+    if (p) cudaFree(p);
+  for (int* p : ctx->gather_ibuf)
+    if (p) cudaFree(p);
+  for (ncclComm_t c : ctx->comms)
+    if (c) ctx->nccl.CommDestroy(c);
   for (auto& d : ctx->devs) free_device(d);
   delete ctx;
   return PSA_OK;
@@ -585,14 +630,23 @@ static int set_matrix_common(Context* ctx, const double* T, int64_t ldt, int m, 
   PSA_CUDA(cudaMemcpy2DAsync(d0.T, (size_t)m * 16, T, (size_t)ldt * 16, (size_t)m * 16, n,
                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, d0.stream));
   PSA_CUDA(cudaStreamSynchronize(d0.stream));
-  for (size_t i = 1; i < ctx->devs.size(); ++i) {
-    Device& d = ctx->devs[i];
-    PSA_CUDA(cudaSetDevice(d.dev));
-    if (d.T_cap < (size_t)m * n) {
-      if ((rc = dev_alloc(ctx, &d.T, (size_t)m * n))) return rc;
-      d.T_cap = (size_t)m * n;
+  if (ctx->devs.size() > 1) {
+    // replicate T with one NCCL broadcast over NVLink (root = device 0)
+    if ((rc = ensure_comms(ctx))) return rc;
+    for (size_t i = 1; i < ctx->devs.size(); ++i) {
+      Device& d = ctx->devs[i];
+      PSA_CUDA(cudaSetDevice(d.dev));
+      if (d.T_cap < (size_t)m * n) {
+        if ((rc = dev_alloc(ctx, &d.T, (size_t)m * n))) return rc;
+        d.T_cap = (size_t)m * n;
+      }
     }
-    PSA_CUDA(cudaMemcpyPeerAsync(d.T, d.dev, d0.T, d0.dev, (size_t)m * n * 16, d.stream));
+    PSA_NCCL(ctx->nccl.GroupStart());
+    for (size_t i = 0; i < ctx->devs.size(); ++i) {
+      Device& d = ctx->devs[i];
+      PSA_NCCL(ctx->nccl.Broadcast(d0.T, d.T, (size_t)m * n * 2, ncclDouble, 0, ctx->comms[i], d.stream));
+    }
+    PSA_NCCL(ctx->nccl.GroupEnd());
   }
   ctx->algo = algo;
   for (auto& d : ctx->devs)
@@ -644,28 +698,58 @@ int psa_gpu_grid(void* vctx, const double* x, int lx, const double* y, int ly, c
   rc = run_grid(ctx, g, Zout, itout, counts);
   if (rc != PSA_OK) return rc;
   // gather: device i owns rows i, i+ng, ... ; local layout is rows_i x lx column-major
+  Device& d0 = ctx->devs[0];
+  if (ng == 1) {
+    const size_t P = (size_t)ly * lx;
+    PSA_CUDA(cudaSetDevice(d0.dev));
+    PSA_CUDA(cudaMemcpy(Z, d0.Z, P * sizeof(double), cudaMemcpyDeviceToHost));
+    if (iters) PSA_CUDA(cudaMemcpy(iters, d0.iters, P * sizeof(int), cudaMemcpyDeviceToHost));
+    return PSA_OK;
+  }
+  // the sigma_min tiles travel to device 0 over NVLink (grouped ncclSend/ncclRecv), then one D2H per tile
+  PSA_CUDA(cudaSetDevice(d0.dev));
+  for (int i = 1; i < ng; ++i) {
+    const size_t P = (size_t)((ly - i + ng - 1) / ng) * lx;
+    if (ctx->gather_cap[i] < P) {
+      if ((rc = dev_alloc(ctx, &ctx->gather_buf[i], P))) return rc;
+      if ((rc = dev_alloc(ctx, &ctx->gather_ibuf[i], P))) return rc;
+      ctx->gather_cap[i] = P;
+    }
+  }
+  PSA_NCCL(ctx->nccl.GroupStart());
+  for (int i = 1; i < ng; ++i) {
+    Device& d = ctx->devs[i];
+    const size_t P = (size_t)((ly - i + ng - 1) / ng) * lx;
+    if (P == 0) continue;
+    PSA_NCCL(ctx->nccl.Send(d.Z, P, ncclDouble, 0, ctx->comms[i], d.stream));
+    PSA_NCCL(ctx->nccl.Recv(ctx->gather_buf[i], P, ncclDouble, i, ctx->comms[0], d0.stream));
+    if (iters) {
+      PSA_NCCL(ctx->nccl.Send(d.iters, P, ncclInt32, 0, ctx->comms[i], d.stream));
+      PSA_NCCL(ctx->nccl.Recv(ctx->gather_ibuf[i], P, ncclInt32, i, ctx->comms[0], d0.stream));
+    }
+  }
+  PSA_NCCL(ctx->nccl.GroupEnd());
+  for (int i = 1; i < ng; ++i) {
+    PSA_CUDA(cudaSetDevice(ctx->devs[i].dev));
+    PSA_CUDA(cudaStreamSynchronize(ctx->devs[i].stream));
+  }
+  PSA_CUDA(cudaSetDevice(d0.dev));
+  PSA_CUDA(cudaStreamSynchronize(d0.stream));
   std::vector<double> zb;
   std::vector<int> ib;
   for (int i = 0; i < ng; ++i) {
-    Device& d = ctx->devs[i];
-    PSA_CUDA(cudaSetDevice(d.dev));
     const int rows = (ly - i + ng - 1) / ng;
     const size_t P = (size_t)rows * lx;
     if (P == 0) continue;
-    if (ng == 1) {
-      PSA_CUDA(cudaMemcpy(Z, d.Z, P * sizeof(double), cudaMemcpyDeviceToHost));
-      if (iters) PSA_CUDA(cudaMemcpy(iters, d.iters, P * sizeof(int), cudaMemcpyDeviceToHost));
-    } else {
-      zb.resize(P);
-      PSA_CUDA(cudaMemcpy(zb.data(), d.Z, P * sizeof(double), cudaMemcpyDeviceToHost));
+    zb.resize(P);
+    PSA_CUDA(cudaMemcpy(zb.data(), i == 0 ? d0.Z : ctx->gather_buf[i], P * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < lx; ++k)
+      for (int jr = 0; jr < rows; ++jr) Z[(size_t)k * ly + i + (size_t)jr * ng] = zb[(size_t)k * rows + jr];
+    if (iters) {
+      ib.resize(P);
+      PSA_CUDA(cudaMemcpy(ib.data(), i == 0 ? d0.iters : ctx->gather_ibuf[i], P * sizeof(int), cudaMemcpyDeviceToHost));
       for (int k = 0; k < lx; ++k)
-        for (int jr = 0; jr < rows; ++jr) Z[(size_t)k * ly + i + (size_t)jr * ng] = zb[(size_t)k * rows + jr];
-      if (iters) {
-        ib.resize(P);
-        PSA_CUDA(cudaMemcpy(ib.data(), d.iters, P * sizeof(int), cudaMemcpyDeviceToHost));
-        for (int k = 0; k < lx; ++k)
-          for (int jr = 0; jr < rows; ++jr) iters[(size_t)k * ly + i + (size_t)jr * ng] = ib[(size_t)k * rows + jr];
-      }
+        for (int jr = 0; jr < rows; ++jr) iters[(size_t)k * ly + i + (size_t)jr * ng] = ib[(size_t)k * rows + jr];
     }
   }
   return PSA_OK;

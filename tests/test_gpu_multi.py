@@ -1,0 +1,50 @@
+"""Multi-device contexts (psa_gpu_init(ngpus > 1)): rows dealt cyclically over the devices of ONE process, T replicated
+by NCCL broadcast, sigma_min tiles gathered on device 0 over NCCL.  Needs >= 2 GPUs (gpurun --gpus 2); skipped on a
+single-GPU box.  Results must be bitwise identical to the single-device context (points are independent)."""
+import numpy as np
+import pytest
+
+import psa_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("ly,lx", [(7, 5), (40, 33)])
+def test_two_device_context_matches_single_device(pkg, ly, lx):
+    T, eigA = po.complex_schur(po.random_complex(300, 4))
+    x, y = np.linspace(-25, 25, lx), np.linspace(-20, 20, ly)
+    q0 = po.start_vector(300, 0)
+    with pkg.PsaGpu(1) as g1:
+        g1.set_matrix(T)
+        Z1, it1, c1, a1 = g1.grid(x, y, q0)
+    ng = min(_ngpus(), 4)
+    with pkg.PsaGpu(ng) as g2:
+        g2.set_matrix(T)
+        Z2, it2, c2, a2 = g2.grid(x, y, q0)
+        Z3, _, _, _ = g2.grid(x[:3], y[:1], q0)  # fewer rows than devices
+    assert a1 == a2 == "sq_lanc"
+    assert np.array_equal(Z1, Z2) and np.array_equal(it1, it2) and np.array_equal(c1, c2)
+    assert np.array_equal(Z3, Z1[:1, :3])
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+def test_two_device_hessqr(pkg):
+    H = np.asfortranarray(po.grcar(210)[:, :-1]).astype(complex)
+    x, y = np.linspace(-1, 3, 6), np.linspace(-3, 3, 5)
+    q0 = po.start_vector(209, 1)
+    with pkg.PsaGpu(1) as g1:
+        g1.set_matrix(H)
+        Z1, it1, _, _ = g1.grid(x, y, q0)
+    with pkg.PsaGpu(2) as g2:
+        g2.set_matrix(H)
+        Z2, it2, _, algo = g2.grid(x, y, q0)
+    assert algo == "HessQR" and np.array_equal(Z1, Z2) and np.array_equal(it1, it2)
