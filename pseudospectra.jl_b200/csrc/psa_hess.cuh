@@ -10,7 +10,7 @@
 namespace psa {
 
 constexpr int HQ_MAX_N = 1024;   // one thread per column in the QR sweep
-constexpr int HS_THREADS = 256;  // solve kernel
+constexpr int HS_THREADS = 128;  // solve kernel (small CTAs: more slots in flight per SM)
 constexpr int HB = 32;           // diagonal block of the per-shift triangular solves
 
 inline size_t hess_R_elems(int n) { return (size_t)n * n; }  // column-major n x n per slot, ld = n
