@@ -7,7 +7,7 @@ LIB := $(PKG)/libpsagpu.so
 
 all: $(LIB) oracle
 
-$(LIB): $(CSRC)/psa_api.cu $(CSRC)/psa_square.cuh $(CSRC)/psa_hess.cuh $(CSRC)/psa_common.cuh include/psa_gpu.h
+$(LIB): $(wildcard $(CSRC)/*.cu $(CSRC)/*.cuh $(CSRC)/*.h) include/psa_gpu.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/psa_api.cu -ldl
 
 oracle:

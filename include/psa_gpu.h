@@ -37,6 +37,8 @@ extern "C" {
 #define PSA_ALGO_NONE 0
 #define PSA_ALGO_SQ_LANC 1 /* :sq_lanc -- square upper-triangular T, m == n >= minlancs4psa (55)     */
 #define PSA_ALGO_HESSQR 2  /* :HessQR  -- rectangular Hessenberg, bw == 2 and m > maxstdqr4hess (200) */
+#define PSA_ALGO_RECT_QR 3 /* :rect_qr -- rectangular (n+1) x n upper Hessenberg with m <= 200 (compute.jl:588-590)   */
+#define PSA_ALGO_SVD 4     /* :SVD     -- n < minlancs4psa (55): smallest singular value directly (compute.jl:478-519) */
 
 /* indices into the counts[] array returned by psa_gpu_grid */
 #define PSA_COUNT_NONCONVERGED 0 /* points where Lanczos hit maxit: shim raises the warning of compute.jl:603-606 */
@@ -67,7 +69,11 @@ int psa_gpu_init(int ngpus, const int* device_ids, void** ctx);
  *   m == n : T is upper triangular (`UpperTriangular{ComplexF64}` parent array); only i <= j is read, exactly
  *            as `UpperTriangular` ignores the strict lower part (compute.jl:600).                 -> :sq_lanc
  *   m == n+1, m > 200 : rectangular Hessenberg (xeigs.jl:226), lower bandwidth 2.                  -> :HessQR
- *   anything else (n < 55 SVD branch, rect_qr, generalised S != I) -> PSA_ERR_UNSUPPORTED.
+ *   m == n+1, m <= 200, upper Hessenberg : the reference's `qr(T1)` branch (compute.jl:588-590).    -> :rect_qr
+ *       (new_matrix only routes Hessenberg input here; dense non-Hessenberg rectangular input is turned into a
+ *        generalised problem by rect_fact, src/Pseudospectra.jl:288-296, and stays on the host.)
+ *   n < 55, m*n <= 12288 : per-point SVD, Z = sigma_min directly (compute.jl:510-518).              -> :SVD
+ *   anything else (generalised S != I, non-Hessenberg rectangular, ...) -> PSA_ERR_UNSUPPORTED.
  * T: column-major, leading dimension ldt (>= m), interleaved complex128. */
 int psa_gpu_set_matrix(void* ctx, const double* T, int64_t ldt, int m, int n);
 

@@ -16,7 +16,7 @@ const libpsagpu = get(ENV, "PSAGPU_LIB", "libpsagpu.so")
 const PSA_OK = Cint(0)
 const PSA_ERR_CANCELLED = Cint(-3)
 const PSA_ERR_UNSUPPORTED = Cint(-4)
-const ALGO = Dict(Cint(1) => :sq_lanc, Cint(2) => :HessQR)
+const ALGO = Dict(Cint(1) => :sq_lanc, Cint(2) => :HessQR, Cint(3) => :rect_qr, Cint(4) => :SVD)
 
 mutable struct Context
     ptr::Ptr{Cvoid}

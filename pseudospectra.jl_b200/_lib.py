@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("PSA_LIB_PATH") or os.path.join(_HERE, "libpsagpu.so")
 PSA_OK = 0
 PSA_ERR_ARG, PSA_ERR_CUDA, PSA_ERR_CANCELLED, PSA_ERR_UNSUPPORTED = -1, -2, -3, -4
 PSA_ERR_NODEVICE, PSA_ERR_NOMATRIX, PSA_ERR_NCCL, PSA_ERR_NOMEM = -5, -6, -7, -8
-ALGO_NAMES = {0: None, 1: "sq_lanc", 2: "HessQR"}
+ALGO_NAMES = {0: None, 1: "sq_lanc", 2: "HessQR", 3: "rect_qr", 4: "SVD"}
 NCOUNTS = 4
 NSTATS = 8
 STAT_NAMES = ("solve_ms", "solve_launches", "total_launches", "grid_ms", "ticks", "flops", "bytes", "pack_ms")

@@ -53,8 +53,6 @@ def psacore(T, S, q0, x, y, bw, *, tol=1e-5, threaded=False, nt=None, warned=Non
     m, n = T.shape
     if m < n:
         raise ValueError("Matrix size must be m x n with m >= n")  # compute.jl:459-461
-    if m != n and bw != 2:
-        raise NotImplementedError("rectangular non-Hessenberg input (rect_qr) is not on the GPU path")
     own = ctx is None
     if own:
         ctx = _context(ngpus)

@@ -18,6 +18,7 @@
 #include "psa_hess.cuh"
 #include "psa_nccl.h"
 #include "psa_square.cuh"
+#include "psa_svd.cuh"
 
 namespace {
 
@@ -152,7 +153,7 @@ void free_device(Device& d) {
 
 int ensure_slots(Context* ctx, Device& d, int want_W) {
   const size_t vec_elems = (size_t)ctx->n_pad;
-  const bool hess = ctx->algo == PSA_ALGO_HESSQR;
+  const bool hess = ctx->algo == PSA_ALGO_HESSQR || ctx->algo == PSA_ALGO_RECT_QR;
   const size_t r_elems = hess ? hess_R_elems(ctx->n) : 0;
   if (d.W >= want_W && d.vec_elems == vec_elems && d.R_elems == r_elems) return PSA_OK;
   PSA_CUDA(cudaSetDevice(d.dev));
@@ -187,7 +188,7 @@ int ensure_slots(Context* ctx, Device& d, int want_W) {
 
 int slot_capacity(const Context* ctx, const Device& d, long long points) {
   long long cap;
-  if (ctx->algo == PSA_ALGO_HESSQR) {
+  if (ctx->algo == PSA_ALGO_HESSQR || ctx->algo == PSA_ALGO_RECT_QR) {
     cap = hess_slot_capacity(ctx->n, d.num_sms);
   } else {
     cap = 2LL * d.num_sms * NS;  // two resident solve CTAs per SM, NS shifts each
@@ -314,7 +315,9 @@ int prepare_matrix(Context* ctx, Device& d) {
   return PSA_OK;  // slot buffers are re-validated by ensure_slots (they depend on n_pad / algo)
 }
 
-int classify(int m, int n) {
+int classify(int m, int n, bool is_hessenberg) {
+  if (n < 55) return (long long)m * n <= SVD_MAX_ELEMS ? PSA_ALGO_SVD : PSA_ALGO_NONE;  // compute.jl:478
+  if (m == n + 1 && m <= 200 && is_hessenberg) return PSA_ALGO_RECT_QR;                 // compute.jl:588-590
   if (m == n && n >= 55) return PSA_ALGO_SQ_LANC;        // compute.jl:478,534,565,594
   if (m == n + 1 && m > 200 && n <= HQ_MAX_N) return PSA_ALGO_HESSQR;  // compute.jl:579 (bw == 2 is the caller's promise)
   return PSA_ALGO_NONE;
@@ -343,8 +346,10 @@ int run_grid(Context* ctx, const GridArgs& g, std::vector<double*>& Zout, std::v
     rows[i] = (g.ly - i + ng - 1) / ng;
     P[i] = rows[i] * g.lx;
     PSA_CUDA(cudaSetDevice(d.dev));
-    if ((rc = ensure_slots(ctx, d, slot_capacity(ctx, d, P[i])))) return rc;
-    PSA_CUDA(cudaMemsetAsync(d.slot_point, 0xff, (d.W + 1) * sizeof(int), d.stream));
+    if (ctx->algo != PSA_ALGO_SVD) {  // the SVD branch has no Lanczos state
+      if ((rc = ensure_slots(ctx, d, slot_capacity(ctx, d, P[i])))) return rc;
+      PSA_CUDA(cudaMemsetAsync(d.slot_point, 0xff, (d.W + 1) * sizeof(int), d.stream));
+    }
     PSA_CUDA(cudaMemsetAsync(d.state, 0, 4 * sizeof(int), d.stream));
     PSA_CUDA(cudaMemsetAsync(d.counts, 0, PSA_NCOUNTS * sizeof(unsigned long long), d.stream));
     PSA_CUDA(cudaEventRecord(d.g0, d.stream));
@@ -374,6 +379,36 @@ int run_grid(Context* ctx, const GridArgs& g, std::vector<double*>& Zout, std::v
                                                          0, 32, d.stream));
       order[i] = d.ord_out;
       launches += 2;
+    }
+  }
+  if (ctx->algo == PSA_ALGO_SVD) {
+    // no Lanczos, no slots: one launch per device over all of its points
+    for (int i = 0; i < ng; ++i) {
+      Device& d = ctx->devs[i];
+      PSA_CUDA(cudaSetDevice(d.dev));
+      PSA_CUDA(cudaFuncSetAttribute(svd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      if (P[i] == 0) continue;
+      SvdParams sp;
+      sp.m = ctx->m;
+      sp.n = ctx->n;
+      sp.T = d.T;
+      sp.P = P[i];
+      sp.rows_local = rows[i];
+      sp.row0 = i;
+      sp.row_step = ng;
+      sp.x = d.x;
+      sp.y = d.y;
+      sp.Z = Zout[i];
+      sp.iters = itout[i];
+      sp.counts = d.counts;
+      EventPair& ep = event_pair(d, nev[i]++);
+      PSA_CUDA(cudaEventRecord(ep.a, d.stream));
+      svd_kernel<<<std::min(P[i], 8 * d.num_sms), SVD_THREADS, svd_smem(ctx->m, ctx->n), d.stream>>>(sp);
+      PSA_CUDA(cudaEventRecord(ep.b, d.stream));
+      PSA_CUDA(cudaGetLastError());
+      launches += 1;
+      solve_launches += (i == 0);
+      done[i] = 1;
     }
   }
   const int hist_maxit = std::min(g.maxit, HIST - 2);
@@ -454,6 +489,7 @@ int run_grid(Context* ctx, const GridArgs& g, std::vector<double*>& Zout, std::v
         ht.Wv = d.Wv;
         ht.sel = d.slot_sel;
         ht.z = d.slot_z;
+        ht.full_sweep = ctx->algo == PSA_ALGO_RECT_QR;
         PSA_CUDA(cudaEventRecord(ep.a, d.stream));
         const int nl = hess_launch_tick(ht, d.stream, ep.a, ep.b);
         launches += nl;
@@ -612,7 +648,26 @@ int psa_gpu_free(void* vctx) {
 
 static int set_matrix_common(Context* ctx, const double* T, int64_t ldt, int m, int n, bool on_device) {
   if (!T || m < n || n < 1 || ldt < m) return PSA_ERR_ARG;
-  const int algo = classify(m, n);
+  bool is_hess = false;
+  if (m == n + 1 && m <= 200 && n >= 55) {  // rect_qr candidates: is the input upper Hessenberg?
+    std::vector<double> host;
+    const double* Th = T;
+    if (on_device) {
+      host.resize((size_t)m * n * 2);
+      PSA_CUDA(cudaSetDevice(ctx->devs[0].dev));
+      PSA_CUDA(cudaMemcpy2D(host.data(), (size_t)m * 16, T, (size_t)ldt * 16, (size_t)m * 16, n, cudaMemcpyDeviceToHost));
+      Th = host.data();
+    }
+    const int64_t ld = on_device ? m : ldt;
+    is_hess = true;
+    for (int j = 0; j < n && is_hess; ++j)
+      for (int i = j + 2; i < m; ++i)
+        if (Th[2 * (i + j * ld)] != 0.0 || Th[2 * (i + j * ld) + 1] != 0.0) {
+          is_hess = false;
+          break;
+        }
+  }
+  const int algo = classify(m, n, is_hess);
   if (algo == PSA_ALGO_NONE) return PSA_ERR_UNSUPPORTED;
   ctx->algo = PSA_ALGO_NONE;
   ctx->m = m;

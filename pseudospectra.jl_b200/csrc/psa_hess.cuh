@@ -47,9 +47,13 @@ __device__ __forceinline__ void givens_cs(double2 f, double2 g, double& c, doubl
 // One CTA per freshly scheduled slot, one thread per column c.  The thread keeps the running entry of row
 // jj ("carry") in a register: rotation jj turns (carry, T1[jj+1,c]) into the final R[jj,c] and the next carry.
 // Column jj's owner produces the rotation; it is broadcast through (double-buffered) shared memory.
+// full_sweep = 0: :HessQR, rotations jj = 1..n-1 only (the reference's loop bound, compute.jl:581).
+// full_sweep = 1: :rect_qr on Hessenberg input: the reference calls qr(T1) (compute.jl:589), which also
+//   eliminates H[n+1,n]; for an upper Hessenberg matrix that is one more rotation, and R is unique up to unit row
+//   phases, which leave (R^H R) and hence sigma unchanged.
 __global__ void hess_qr_kernel(const int* __restrict__ fresh, int m, int n, const double2* __restrict__ H,
                                const double2* __restrict__ zs, double2* __restrict__ Rall,
-                               const double2* __restrict__ q0, int n_pad, double2* __restrict__ Q0) {
+                               const double2* __restrict__ q0, int n_pad, double2* __restrict__ Q0, int full_sweep) {
   __shared__ double g_c[2];
   __shared__ double2 g_s[2];
   const int slot = fresh[blockIdx.x];
@@ -103,7 +107,19 @@ __global__ void hess_qr_kernel(const int* __restrict__ fresh, int m, int n, cons
       carry = nc;
     }
   }
-  if (c == n - 1) R[(size_t)c * n + (n - 1)] = carry;  // H[n+1,n] is never rotated in (reference quirk)
+  if (c == n - 1) {
+    if (full_sweep) {
+      const double2 b = Hc[n];  // row n+1 of the (n+1) x n matrix
+      double cs;
+      double2 sn;
+      givens_cs(carry, b, cs, sn);
+      double2 r = cmul(sn, b);
+      r.x = fma(cs, carry.x, r.x);
+      r.y = fma(cs, carry.y, r.y);
+      carry = r;
+    }
+    R[(size_t)c * n + (n - 1)] = carry;  // HessQR: H[n+1,n] is never rotated in (reference quirk)
+  }
 }
 
 // One CTA per active slot: w = R^{-H} q (forward, dot form) then v = R^{-1} w (backward, axpy form); v -> Wv.
@@ -223,6 +239,7 @@ struct HessTick {
   double2 *Q0, *Q1, *Wv;
   const int* sel;
   const double2* z;
+  int full_sweep;
 };
 
 inline size_t hess_solve_smem(int n_pad) { return ((size_t)n_pad + HB * (HB + 1) + HB) * sizeof(double2); }
@@ -238,7 +255,7 @@ inline int hess_launch_tick(const HessTick& t, cudaStream_t stream, cudaEvent_t 
   int launches = 0;
   if (t.n_fresh > 0) {
     const int threads = (t.n + 31) / 32 * 32;
-    hess_qr_kernel<<<t.n_fresh, threads, 0, stream>>>(t.fresh, t.m, t.n, t.H, t.z, t.R, t.q0, t.n_pad, t.Q0);
+    hess_qr_kernel<<<t.n_fresh, threads, 0, stream>>>(t.fresh, t.m, t.n, t.H, t.z, t.R, t.q0, t.n_pad, t.Q0, t.full_sweep);
     ++launches;
   }
   HessSolveParams sp;

@@ -166,11 +166,52 @@ def test_edge_shapes_and_reuse(gpu):
         assert _rel(Z2, Zc2) < RTOL
 
 
+def test_svd_branch_small_matrices(gpu):
+    """n < 55 -> :SVD, Z = sigma_min directly (compute.jl:510-518); incl. the reference's own smoke input
+    (test/runtests.jl:8-13: 32x32 real triu(rand)), a complex dense, an odd n and a rectangular case."""
+    rng = np.random.default_rng(3)
+    cases = [np.triu(rng.random((32, 32))), rng.standard_normal((40, 40)) + 1j * rng.standard_normal((40, 40)),
+             rng.standard_normal((17, 17)) + 0j, rng.standard_normal((60, 50)) + 1j * rng.standard_normal((60, 50)),
+             po.grcar(54)]
+    x, y = np.linspace(-1.5, 2.5, 9), np.linspace(-2.0, 2.0, 7)
+    for A in cases:
+        gpu.set_matrix(A)
+        Z, it, counts, algo = gpu.grid(x, y, np.ones(A.shape[1]))
+        Zo, algo_o, _ = po.psacore(A, np.ones(A.shape[1]), x, y, A.shape[0] - A.shape[1] + 1)
+        assert algo == "SVD" == algo_o and counts[3] == 63 and it.max() == 0
+        nrm = np.linalg.norm(A, 2)
+        assert np.max(np.abs(Z - Zo)) <= 1e-12 * nrm          # absolute accuracy of any backward-stable SVD
+        ok = Zo > 1e-8 * nrm
+        assert _rel(Z[ok], Zo[ok], 0.0) < RTOL
+
+
+def test_rect_qr_small_hessenberg(gpu):
+    """test/smrect.jl: grcar(190)[:,1:end-1] (m <= 200, Hessenberg) -> :rect_qr (compute.jl:588-590)."""
+    A = np.asfortranarray(po.grcar(190)[:, :-1]).astype(complex)
+    x, y = np.linspace(-1.0, 3.0, 8), np.linspace(-3.0, 3.0, 7)
+    q0 = po.start_vector(189, 5)
+    gpu.set_matrix(A)
+    Z, it, counts, algo = gpu.grid(x, y, q0)
+    Zo, algo_o, _, ito = po.psacore(A, q0, x, y, 2, want_iters=True)
+    assert algo == "rect_qr" == algo_o
+    assert _rel(Z, Zo, _floor(A)) < RTOL and np.mean(it == ito) > 0.95
+    # ARPACK-default-sized projection (ncv = 60 -> 61 x 60 Hessenberg), test/swmethod.jl:24
+    H = po.arnoldi_hessenberg(po.convdiff_fd(4), 60, seed=1)
+    ev = np.linalg.eigvals(H[:60, :])
+    xs, ys, _ = po.make_grid(po.vec2ax(ev), 10, False)
+    q1 = po.start_vector(60, 2)
+    gpu.set_matrix(H)
+    Z, it, counts, algo = gpu.grid(xs, ys, q1)
+    Zo, algo_o, _, ito = po.psacore(H, q1, xs, ys, 2, want_iters=True)
+    assert algo == "rect_qr" == algo_o and _rel(Z, Zo, _floor(H)) < RTOL
+
+
 def test_unsupported_shapes_raise(pkg, gpu):
+    A = np.ones((190, 189))
     with pytest.raises(pkg.PsaGpuUnsupported):
-        gpu.set_matrix(np.triu(np.ones((32, 32))))  # n < 55: SVD branch stays on the host (compute.jl:478)
+        gpu.set_matrix(A)  # rectangular but not Hessenberg: rect_fact makes it a generalised problem (host path)
     with pytest.raises(pkg.PsaGpuUnsupported):
-        gpu.set_matrix(np.ones((190, 189)))  # m <= 200: rect_qr (compute.jl:588-590)
+        gpu.set_matrix(np.ones((300, 250)))  # bw > 2
     with pytest.raises(pkg.PsaGpuError):
         pkg.PsaGpu(1).grid([0.0], [0.0], np.ones(4))  # no matrix set
 
