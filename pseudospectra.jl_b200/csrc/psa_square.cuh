@@ -22,10 +22,10 @@ constexpr int XROW_BYTES = KC * 16 + 64;      // 320: X smem row stride (64 B pa
 constexpr int STAGES = 3;                     // <= 4 (producer/consumer distance rule)
 constexpr int SOLVE_THREADS = 256;
 // per panel width NSV (64, 32 or 16 shifts per CTA): X tile NSV rows, ring of STAGES (T tile + X tile) stages,
-// then mbarriers (32 B reserved) + shifts + 2 pointer tables
+// then mbarriers (64 B reserved) + shifts + 2 pointer tables
 __host__ __device__ constexpr int stage_bytes(int nsv) { return TILE_BYTES + nsv * XROW_BYTES; }
-__host__ __device__ constexpr int solve_smem(int nsv) { return STAGES * stage_bytes(nsv) + 32 + nsv * 16 + nsv * 8 * 2; }
-static_assert(STAGES * 8 <= 32, "mbarrier block");
+__host__ __device__ constexpr int solve_smem(int nsv) { return STAGES * stage_bytes(nsv) + 64 + nsv * 16 + nsv * 8 * 2; }
+static_assert(2 * STAGES * 8 <= 64, "mbarrier block");
 constexpr int HIST = 128;                     // per-slot alpha/beta history stride (maxit <= 126)
 
 __host__ __device__ inline long long tiles_per_phase(int nblk) { return 2LL * nblk * (nblk + 1); }
@@ -156,8 +156,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_kernel(SolveParams P) 
   const int panel = blockIdx.x;
   if (panel * NSV >= n_active) return;
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // 32 B reserved
-  double2* zsh = reinterpret_cast<double2*>(smem + STAGES * STAGE_BYTES + 32);    // 16 B aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // 64 B reserved
+  double2* zsh = reinterpret_cast<double2*>(smem + STAGES * STAGE_BYTES + 64);    // 16 B aligned
   double2** wptr = reinterpret_cast<double2**>(zsh + NSV);
   const double2** qptr = (const double2**)(wptr + NSV);
 
@@ -172,7 +172,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_kernel(SolveParams P) 
   }
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1 + SOLVE_THREADS);  // thread 0 expect_tx + one cp.async arrival per thread
+    }
     mbar_fence_init();
   }
   __syncthreads();
@@ -181,23 +183,29 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_kernel(SolveParams P) 
   const int steps_per_phase = (int)tiles_per_phase(nblk);
   const int total_steps = 2 * steps_per_phase;
 
-  // producer side: issue the loads of one step into its ring stage.  Called by ALL warps: a bulk copy is a
-  // uniform-datapath instruction (UBLKCP), so per-lane copies are serialised inside a warp; spreading the NSV row
-  // copies over the 8 warps keeps that serial issue off any single warp's critical path.
+  // producer side: issue the loads of one step into its ring stage; called by ALL threads.
+  //  * T tile: one 16 KiB bulk copy through the TMA engine (thread 0), completing by bytes on the stage mbarrier;
+  //  * X tile: NSV rows of 256 B, one row per shift at a scattered address.  A bulk copy is a uniform-datapath
+  //    instruction (UBLKCP), so per-lane bulk copies are serialised (~80 clk each); instead every thread issues
+  //    16-byte cp.async copies (LDGSTS) for its share of the rows and hooks their completion onto the same
+  //    mbarrier (one pre-counted arrival per thread).
   auto issue = [&](const StepCursor& pc, int stage) {
-    constexpr int RPW = NSV / (SOLVE_THREADS / 32);  // X rows issued per warp
     unsigned char* sb = smem + stage * STAGE_BYTES;
     const bool needX = pc.c < CPB * pc.I;
     if (tid == 0) {
-      mbar_arrive_expect_tx(&full_bar[stage], TILE_BYTES + (needX ? NSV * KC * 16 : 0));
+      mbar_arrive_expect_tx(&full_bar[stage], TILE_BYTES);
       const double2* src = (pc.phase ? P.packB : P.packA) + tile_index(pc.I, pc.c) * TILE_ELEMS;
       bulk_g2s(sb, src, TILE_BYTES, &full_bar[stage]);
     }
-    if (needX && lane < RPW) {
+    if (needX) {
       const int mem0 = pc.phase ? n_pad - KC * pc.c - KC : KC * pc.c;
-      const int s = warp * RPW + lane;
-      bulk_g2s(sb + TILE_BYTES + s * XROW_BYTES, wptr[s] + mem0, KC * 16, &full_bar[stage]);
+#pragma unroll
+      for (int seg = tid; seg < NSV * KC; seg += SOLVE_THREADS) {  // 16-byte segments: row = seg / KC
+        const int s = seg / KC, part = seg % KC;
+        cp_async16(sb + TILE_BYTES + s * XROW_BYTES + part * 16, wptr[s] + mem0 + part);
+      }
     }
+    cp_async_mbar_arrive_noinc(&full_bar[stage]);  // arrives once this thread's copies (if any) have landed
   };
 
   double cre[2][NT][2], cim[2][NT][2];
@@ -319,7 +327,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_kernel(SolveParams P) 
             op_[r ^ flip] = b[r];
           }
         }
-        fence_proxy_async();  // the next block rows read these x through the async proxy
+        fence_proxy_async();  // belt and braces: later block rows re-read these x with asynchronous copies
       }
       __syncthreads();
       if (wm > cp) gemm_step(sb, flip);
