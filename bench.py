@@ -19,6 +19,12 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 to every worker.  Rank 0 performs the one-time host Schur reduction and must
+# use the host's cores for it; this has to be set before numpy/scipy load their BLAS.
+_RANK0 = int(os.environ.get("RANK", "0")) == 0
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ[_v] = str((os.cpu_count() or 1) if _RANK0 else 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -221,12 +227,30 @@ def run_ours(args):
         T_host.copy_(torch.from_numpy(T.T))
         log(f"[bench] schur {how} in {schur_s:.1f} s")
     T_dev = torch.empty((n, n), dtype=torch.complex128, device=dev)
+    # the other ranks sleep (instead of spinning inside the NCCL broadcast) until rank 0 has finished the host
+    # reduction, so that they do not compete with it for the host cores
+    flag = os.path.join(os.environ.get("PSA_BENCH_CACHE", "/tmp/psa_b200_cache"),
+                        "ready_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid()))  # ppid = the torchrun agent
+    if world > 1:
+        if rank == 0:
+            os.makedirs(os.path.dirname(flag), exist_ok=True)
+            open(flag, "w").close()
+        else:
+            while not os.path.exists(flag):
+                time.sleep(0.2)
     t0 = time.time()
     if rank == 0:
         T_dev.copy_(T_host, non_blocking=True)
     sharding.broadcast_matrix(T_dev, 0)
     torch.cuda.synchronize()
     bcast_s = time.time() - t0
+    if world > 1:
+        dist.barrier()
+        if rank == 0:
+            try:
+                os.remove(flag)
+            except OSError:
+                pass
     if rank != 0:
         T_host.copy_(T_dev)  # every rank keeps a pinned host copy for its end-to-end leg
     T_np = T_host.numpy().T  # column-major view (n x n)

@@ -255,7 +255,7 @@ int pick_panel_width(int n_active, int num_sms) {
   const int forced = env ? atoi(env) : 0;
   if (forced == 64 || forced == 48 || forced == 32 || forced == 16) return forced;
   static const int widths[4] = {16, 32, 48, 64};
-  static const double t1[4] = {0.209, 0.331, 0.453, 0.584}, t2[4] = {0.309, 0.538, 0.775, 1.0};
+  static const double t1[4] = {0.205, 0.319, 0.440, 0.560}, t2[4] = {0.308, 0.537, 0.770, 1.0};
   int best = 64;
   double best_cost = 1e300;
   for (int i = 0; i < 4; ++i) {

@@ -13,7 +13,9 @@ constexpr int HQ_MAX_N = 1024;   // one thread per column in the QR sweep
 constexpr int HS_THREADS = 128;  // solve kernel (small CTAs: more slots in flight per SM)
 constexpr int HB = 32;           // diagonal block of the per-shift triangular solves
 
-inline size_t hess_R_elems(int n) { return (size_t)n * n; }  // column-major n x n per slot, ld = n
+// Per-slot storage of the private triangular factor: Rc (column-major n x n), Rr (row-major copy, so that BOTH
+// triangular solves stream contiguous vectors) and rinv (reciprocal diagonal).
+inline size_t hess_R_elems(int n) { return 2 * (size_t)n * n + (size_t)((n + 31) / 32 * 32); }
 // Slots in flight: enough CTAs to keep HBM busy and to amortise the per-tick launches, bounded by a 24 GB budget
 // for the private triangular factors.
 inline long long hess_slot_capacity(int n, int num_sms) {
@@ -59,7 +61,10 @@ __global__ void hess_qr_kernel(const int* __restrict__ fresh, int m, int n, cons
   const int slot = fresh[blockIdx.x];
   const int c = threadIdx.x;
   const double2 z = zs[slot];
-  double2* R = Rall + (size_t)slot * n * n;
+  const size_t rstride = 2 * (size_t)n * n + (size_t)((n + 31) / 32 * 32);
+  double2* R = Rall + (size_t)slot * rstride;   // Rc: R[i,k] at k*n + i
+  double2* Rr = R + (size_t)n * n;               // Rr: R[j,k] at j*n + k
+  double2* rinv = Rr + (size_t)n * n;            // 1 / R[k,k]
   // q <- q0 for this slot
   double2* q = Q0 + (size_t)slot * n_pad;
   for (int i = c; i < n_pad; i += blockDim.x) q[i] = (i < n) ? q0[i] : make_double2(0.0, 0.0);
@@ -100,6 +105,8 @@ __global__ void hess_qr_kernel(const int* __restrict__ fresh, int m, int n, cons
       r.x = fma(cs, a.x, r.x);
       r.y = fma(cs, a.y, r.y);
       R[(size_t)c * n + jj] = r;
+      Rr[(size_t)jj * n + c] = r;
+      if (c == jj) rinv[jj] = crecip(r);
       const double2 sc = make_double2(-sn.x, sn.y);  // -conj(sn)
       double2 nc = cmul(sc, a);
       nc.x = fma(cs, b.x, nc.x);
@@ -119,6 +126,8 @@ __global__ void hess_qr_kernel(const int* __restrict__ fresh, int m, int n, cons
       carry = r;
     }
     R[(size_t)c * n + (n - 1)] = carry;  // HessQR: H[n+1,n] is never rotated in (reference quirk)
+    Rr[(size_t)(n - 1) * n + c] = carry;
+    rinv[n - 1] = crecip(carry);
   }
 }
 
@@ -142,7 +151,7 @@ __global__ void __launch_bounds__(HS_THREADS) hess_solve_kernel(HessSolveParams 
   if ((int)blockIdx.x >= *P.n_active) return;
   const int slot = P.active[blockIdx.x];
   const int n = P.n, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const double2* R = P.R + (size_t)slot * n * n;
+  const double2* R = P.R + (size_t)slot * (2 * (size_t)n * n + (size_t)((n + 31) / 32 * 32));
   const double2* q = (P.sel[slot] ? P.Q1 : P.Q0) + (size_t)slot * P.n_pad;
   const int nb = (n + HB - 1) / HB;
 
@@ -226,6 +235,116 @@ __global__ void __launch_bounds__(HS_THREADS) hess_solve_kernel(HessSolveParams 
   for (int i = tid; i < n; i += HS_THREADS) out[i] = w[i];
 }
 
+// Warp-per-slot variant for n <= 256: the vector lives in registers (8 elements per lane), both solves are
+// "axpy form" (one contiguous row of Rr / column of Rc per step, prefetched one step ahead), the pivot value is
+// broadcast with a shuffle and the diagonal reciprocals come from the QR kernel.  One step costs about one memory
+// latency, so ~16 warps per SM keep HBM busy; there is no block-level synchronisation at all.
+constexpr int HW_NPL = 8;        // vector elements per lane
+constexpr int HW_THREADS = 128;  // 4 slots per CTA
+
+__global__ void __launch_bounds__(HW_THREADS) hess_solve_warp_kernel(HessSolveParams P) {
+  const int lane = threadIdx.x & 31;
+  const int a = blockIdx.x * (HW_THREADS / 32) + (threadIdx.x >> 5);
+  if (a >= *P.n_active) return;
+  const int slot = P.active[a];
+  const int n = P.n;
+  const size_t rstride = 2 * (size_t)n * n + (size_t)((n + 31) / 32 * 32);
+  const double2* Rc = P.R + (size_t)slot * rstride;
+  const double2* Rr = Rc + (size_t)n * n;
+  const double2* rinv = Rr + (size_t)n * n;
+  const double2* q = (P.sel[slot] ? P.Q1 : P.Q0) + (size_t)slot * P.n_pad;
+  const double2 zero = make_double2(0.0, 0.0);
+
+  double2 x[HW_NPL], cur[HW_NPL], nxt[HW_NPL];
+#pragma unroll
+  for (int e = 0; e < HW_NPL; ++e) {
+    const int i = 32 * e + lane;
+    x[e] = i < n ? q[i] : zero;
+  }
+  // ---- forward: (R^H) w = q.  After w_j is final, row j of R updates the entries k > j. ----
+#pragma unroll
+  for (int e = 0; e < HW_NPL; ++e) {
+    const int k = 32 * e + lane;
+    cur[e] = (k > 0 && k < n) ? Rr[k] : zero;  // row 0
+  }
+  double2 rcur = rinv[0];
+#pragma unroll
+  for (int je = 0; je < HW_NPL; ++je) {
+    for (int jl = 0; jl < 32; ++jl) {
+      const int j = 32 * je + jl;
+      if (j >= n) break;
+      // prefetch row j+1 (entries k > j+1) and its diagonal reciprocal
+      const int jn = j + 1;
+      double2 rnext = zero;
+      if (jn < n) {
+        rnext = rinv[jn];
+#pragma unroll
+        for (int e = 0; e < HW_NPL; ++e) {
+          const int k = 32 * e + lane;
+          nxt[e] = (e >= je && k > jn && k < n) ? Rr[(size_t)jn * n + k] : zero;
+        }
+      }
+      const double xr = __shfl_sync(0xffffffffu, x[je].x, jl), xi = __shfl_sync(0xffffffffu, x[je].y, jl);
+      const double2 wj = cmul(make_double2(xr, xi), make_double2(rcur.x, -rcur.y));  // / conj(R[j,j])
+      if (lane == jl) x[je] = wj;
+#pragma unroll
+      for (int e = 0; e < HW_NPL; ++e)
+        if (e >= je) {
+          const int k = 32 * e + lane;
+          if (k > j && k < n) cmsub(x[e], make_double2(cur[e].x, -cur[e].y), wj);  // conj(R[j,k]) * w_j
+        }
+#pragma unroll
+      for (int e = 0; e < HW_NPL; ++e) cur[e] = nxt[e];
+      rcur = rnext;
+    }
+  }
+  // ---- backward: R v = w.  After v_k is final, column k of R updates the entries i < k. ----
+  {
+    const int k0 = n - 1;
+#pragma unroll
+    for (int e = 0; e < HW_NPL; ++e) {
+      const int i = 32 * e + lane;
+      cur[e] = i < k0 ? Rc[(size_t)k0 * n + i] : zero;
+    }
+    rcur = rinv[k0];
+  }
+#pragma unroll
+  for (int ke = HW_NPL - 1; ke >= 0; --ke) {
+    for (int kl = 31; kl >= 0; --kl) {
+      const int k = 32 * ke + kl;
+      if (k >= n) continue;
+      const int kn = k - 1;
+      double2 rnext = zero;
+      if (kn >= 0) {
+        rnext = rinv[kn];
+#pragma unroll
+        for (int e = 0; e < HW_NPL; ++e) {
+          const int i = 32 * e + lane;
+          nxt[e] = (e <= ke && i < kn) ? Rc[(size_t)kn * n + i] : zero;
+        }
+      }
+      const double xr = __shfl_sync(0xffffffffu, x[ke].x, kl), xi = __shfl_sync(0xffffffffu, x[ke].y, kl);
+      const double2 vk = cmul(make_double2(xr, xi), rcur);
+      if (lane == kl) x[ke] = vk;
+#pragma unroll
+      for (int e = 0; e < HW_NPL; ++e)
+        if (e <= ke) {
+          const int i = 32 * e + lane;
+          if (i < k) cmsub(x[e], cur[e], vk);
+        }
+#pragma unroll
+      for (int e = 0; e < HW_NPL; ++e) cur[e] = nxt[e];
+      rcur = rnext;
+    }
+  }
+  double2* out = P.Wv + (size_t)slot * P.n_pad;
+#pragma unroll
+  for (int e = 0; e < HW_NPL; ++e) {
+    const int i = 32 * e + lane;
+    if (i < n) out[i] = x[e];
+  }
+}
+
 struct HessTick {
   int m, n, n_pad;
   const double2* H;
@@ -268,7 +387,10 @@ inline int hess_launch_tick(const HessTick& t, cudaStream_t stream, cudaEvent_t 
   sp.Q1 = t.Q1;
   sp.Wv = t.Wv;
   sp.sel = t.sel;
-  hess_solve_kernel<<<t.n_active, HS_THREADS, hess_solve_smem(t.n_pad), stream>>>(sp);
+  if (t.n <= 32 * HW_NPL)
+    hess_solve_warp_kernel<<<(t.n_active + HW_THREADS / 32 - 1) / (HW_THREADS / 32), HW_THREADS, 0, stream>>>(sp);
+  else
+    hess_solve_kernel<<<t.n_active, HS_THREADS, hess_solve_smem(t.n_pad), stream>>>(sp);
   ++launches;
   cudaEventRecord(ev_b, stream);
   return launches;

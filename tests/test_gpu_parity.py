@@ -120,6 +120,19 @@ def test_hessqr_arnoldi_projection_vs_oracle(gpu):
     assert algo == "HessQR" and _rel(Z, Zc, _floor(H)) < RTOL and np.mean(it == itc) > 0.97
 
 
+def test_hessqr_large_n_uses_block_kernel(gpu):
+    """n > 256: the vector no longer fits the warp-per-slot kernel's registers; the CTA-per-slot solve kernel runs."""
+    rng = np.random.default_rng(11)
+    n = 300
+    H = np.triu(rng.standard_normal((n + 1, n)) + 1j * rng.standard_normal((n + 1, n)), -1)
+    x, y = np.linspace(-3, 3, 5), np.linspace(-3, 3, 4)
+    q0 = po.start_vector(n, 1)
+    gpu.set_matrix(H)
+    Z, it, counts, algo = gpu.grid(x, y, q0)
+    Zc, itc, _ = co.grid(H, x, y, q0, nthreads=8)
+    assert algo == "HessQR" and _rel(Z, Zc, _floor(H)) < RTOL and np.mean(it == itc) > 0.9
+
+
 def test_random_complex_600_vs_oracle_and_svd(gpu):
     T, eigA = po.complex_schur(po.random_complex(600, 1))
     x, y, _ = po.make_grid(po.vec2ax(eigA), 40, False)
