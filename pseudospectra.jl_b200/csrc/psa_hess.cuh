@@ -236,107 +236,116 @@ __global__ void __launch_bounds__(HS_THREADS) hess_solve_kernel(HessSolveParams 
 }
 
 // Warp-per-slot variant for n <= 256: the vector lives in registers (8 elements per lane), both solves are
-// "axpy form" (one contiguous row of Rr / column of Rc per step, prefetched one step ahead), the pivot value is
-// broadcast with a shuffle and the diagonal reciprocals come from the QR kernel.  One step costs about one memory
-// latency, so ~16 warps per SM keep HBM busy; there is no block-level synchronisation at all.
+// "axpy form" (one contiguous row of Rr / column of Rc per step), the pivot value is broadcast with a shuffle and
+// the diagonal reciprocals come from the QR kernel.  The rows stream through a per-warp ring in shared memory
+// filled by cp.async (LDGSTS) HW_DEPTH steps ahead, so a step costs a fraction of a memory latency and ~16 warps
+// per SM keep HBM busy; there is no block-level synchronisation at all.
 constexpr int HW_NPL = 8;        // vector elements per lane
 constexpr int HW_THREADS = 128;  // 4 slots per CTA
+constexpr int HW_DEPTH = 4;      // rows in flight per warp
+
+inline size_t hess_warp_smem(int n) { return (size_t)(HW_THREADS / 32) * HW_DEPTH * ((n + 31) / 32 * 32) * sizeof(double2); }
 
 __global__ void __launch_bounds__(HW_THREADS) hess_solve_warp_kernel(HessSolveParams P) {
-  const int lane = threadIdx.x & 31;
-  const int a = blockIdx.x * (HW_THREADS / 32) + (threadIdx.x >> 5);
+  extern __shared__ __align__(16) unsigned char hwsm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int a = blockIdx.x * (HW_THREADS / 32) + warp;
   if (a >= *P.n_active) return;
   const int slot = P.active[a];
-  const int n = P.n;
-  const size_t rstride = 2 * (size_t)n * n + (size_t)((n + 31) / 32 * 32);
+  const int n = P.n, n32 = (n + 31) / 32 * 32;
+  const size_t rstride = 2 * (size_t)n * n + (size_t)n32;
   const double2* Rc = P.R + (size_t)slot * rstride;
   const double2* Rr = Rc + (size_t)n * n;
   const double2* rinv = Rr + (size_t)n * n;
   const double2* q = (P.sel[slot] ? P.Q1 : P.Q0) + (size_t)slot * P.n_pad;
+  double2* ring = reinterpret_cast<double2*>(hwsm) + (size_t)warp * HW_DEPTH * n32;
   const double2 zero = make_double2(0.0, 0.0);
 
-  double2 x[HW_NPL], cur[HW_NPL], nxt[HW_NPL];
+  double2 x[HW_NPL], ri[HW_NPL];
 #pragma unroll
   for (int e = 0; e < HW_NPL; ++e) {
     const int i = 32 * e + lane;
     x[e] = i < n ? q[i] : zero;
+    ri[e] = i < n ? rinv[i] : zero;
   }
   // ---- forward: (R^H) w = q.  After w_j is final, row j of R updates the entries k > j. ----
+  auto fetch_row = [&](int j) {  // entries k > j of row j -> ring slot j % DEPTH (always commits a group)
+    if (j < n) {
+      double2* dst = ring + (size_t)(j % HW_DEPTH) * n32;
 #pragma unroll
-  for (int e = 0; e < HW_NPL; ++e) {
-    const int k = 32 * e + lane;
-    cur[e] = (k > 0 && k < n) ? Rr[k] : zero;  // row 0
-  }
-  double2 rcur = rinv[0];
+      for (int e = 0; e < HW_NPL; ++e) {
+        const int k = 32 * e + lane;
+        if (k > j && k < n) cp_async16(dst + k, Rr + (size_t)j * n + k);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int d = 0; d < HW_DEPTH; ++d) fetch_row(d);
 #pragma unroll
   for (int je = 0; je < HW_NPL; ++je) {
     for (int jl = 0; jl < 32; ++jl) {
       const int j = 32 * je + jl;
       if (j >= n) break;
-      // prefetch row j+1 (entries k > j+1) and its diagonal reciprocal
-      const int jn = j + 1;
-      double2 rnext = zero;
-      if (jn < n) {
-        rnext = rinv[jn];
-#pragma unroll
-        for (int e = 0; e < HW_NPL; ++e) {
-          const int k = 32 * e + lane;
-          nxt[e] = (e >= je && k > jn && k < n) ? Rr[(size_t)jn * n + k] : zero;
-        }
-      }
+      cp_async_wait<HW_DEPTH - 1>();
+      __syncwarp();
+      const double2* row = ring + (size_t)(j % HW_DEPTH) * n32;
       const double xr = __shfl_sync(0xffffffffu, x[je].x, jl), xi = __shfl_sync(0xffffffffu, x[je].y, jl);
-      const double2 wj = cmul(make_double2(xr, xi), make_double2(rcur.x, -rcur.y));  // / conj(R[j,j])
+      const double rr = __shfl_sync(0xffffffffu, ri[je].x, jl), rim = __shfl_sync(0xffffffffu, ri[je].y, jl);
+      const double2 wj = cmul(make_double2(xr, xi), make_double2(rr, -rim));  // / conj(R[j,j])
       if (lane == jl) x[je] = wj;
 #pragma unroll
       for (int e = 0; e < HW_NPL; ++e)
         if (e >= je) {
           const int k = 32 * e + lane;
-          if (k > j && k < n) cmsub(x[e], make_double2(cur[e].x, -cur[e].y), wj);  // conj(R[j,k]) * w_j
+          if (k > j && k < n) {
+            const double2 r = row[k];
+            cmsub(x[e], make_double2(r.x, -r.y), wj);  // conj(R[j,k]) * w_j
+          }
         }
-#pragma unroll
-      for (int e = 0; e < HW_NPL; ++e) cur[e] = nxt[e];
-      rcur = rnext;
+      __syncwarp();
+      fetch_row(j + HW_DEPTH);
     }
   }
+  cp_async_wait<0>();
+  __syncwarp();
   // ---- backward: R v = w.  After v_k is final, column k of R updates the entries i < k. ----
-  {
-    const int k0 = n - 1;
+  auto fetch_col = [&](int k) {  // entries i < k of column k -> ring slot k % DEPTH
+    if (k >= 0) {
+      double2* dst = ring + (size_t)(k % HW_DEPTH) * n32;
 #pragma unroll
-    for (int e = 0; e < HW_NPL; ++e) {
-      const int i = 32 * e + lane;
-      cur[e] = i < k0 ? Rc[(size_t)k0 * n + i] : zero;
+      for (int e = 0; e < HW_NPL; ++e) {
+        const int i = 32 * e + lane;
+        if (i < k) cp_async16(dst + i, Rc + (size_t)k * n + i);
+      }
     }
-    rcur = rinv[k0];
-  }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int d = 0; d < HW_DEPTH; ++d) fetch_col(n - 1 - d);
 #pragma unroll
   for (int ke = HW_NPL - 1; ke >= 0; --ke) {
     for (int kl = 31; kl >= 0; --kl) {
       const int k = 32 * ke + kl;
       if (k >= n) continue;
-      const int kn = k - 1;
-      double2 rnext = zero;
-      if (kn >= 0) {
-        rnext = rinv[kn];
-#pragma unroll
-        for (int e = 0; e < HW_NPL; ++e) {
-          const int i = 32 * e + lane;
-          nxt[e] = (e <= ke && i < kn) ? Rc[(size_t)kn * n + i] : zero;
-        }
-      }
+      cp_async_wait<HW_DEPTH - 1>();
+      __syncwarp();
+      const double2* col = ring + (size_t)(k % HW_DEPTH) * n32;
       const double xr = __shfl_sync(0xffffffffu, x[ke].x, kl), xi = __shfl_sync(0xffffffffu, x[ke].y, kl);
-      const double2 vk = cmul(make_double2(xr, xi), rcur);
+      const double rr = __shfl_sync(0xffffffffu, ri[ke].x, kl), rim = __shfl_sync(0xffffffffu, ri[ke].y, kl);
+      const double2 vk = cmul(make_double2(xr, xi), make_double2(rr, rim));
       if (lane == kl) x[ke] = vk;
 #pragma unroll
       for (int e = 0; e < HW_NPL; ++e)
         if (e <= ke) {
           const int i = 32 * e + lane;
-          if (i < k) cmsub(x[e], cur[e], vk);
+          if (i < k) cmsub(x[e], col[i], vk);
         }
-#pragma unroll
-      for (int e = 0; e < HW_NPL; ++e) cur[e] = nxt[e];
-      rcur = rnext;
+      __syncwarp();
+      fetch_col(k - HW_DEPTH);
     }
   }
+  cp_async_wait<0>();
   double2* out = P.Wv + (size_t)slot * P.n_pad;
 #pragma unroll
   for (int e = 0; e < HW_NPL; ++e) {
@@ -365,6 +374,8 @@ inline size_t hess_solve_smem(int n_pad) { return ((size_t)n_pad + HB * (HB + 1)
 
 inline int hess_set_attrs() {
   cudaError_t e = cudaFuncSetAttribute(hess_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(hess_solve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hess_warp_smem(32 * HW_NPL));
   return e == cudaSuccess ? 0 : -1;
 }
 
@@ -388,7 +399,7 @@ inline int hess_launch_tick(const HessTick& t, cudaStream_t stream, cudaEvent_t 
   sp.Wv = t.Wv;
   sp.sel = t.sel;
   if (t.n <= 32 * HW_NPL)
-    hess_solve_warp_kernel<<<(t.n_active + HW_THREADS / 32 - 1) / (HW_THREADS / 32), HW_THREADS, 0, stream>>>(sp);
+    hess_solve_warp_kernel<<<(t.n_active + HW_THREADS / 32 - 1) / (HW_THREADS / 32), HW_THREADS, hess_warp_smem(t.n), stream>>>(sp);
   else
     hess_solve_kernel<<<t.n_active, HS_THREADS, hess_solve_smem(t.n_pad), stream>>>(sp);
   ++launches;
