@@ -174,6 +174,69 @@ def recalc_levels(sigmin, ax):
     return levels, 0
 
 
+def _givens(f, g):
+    """(c, s) of Julia's `givensAlgorithm(f, g)` (zlartg convention): [c s; -conj(s) c] [f; g] = [r; 0]."""
+    if g == 0:
+        return 1.0, 0.0 + 0.0j
+    if f == 0:
+        return 0.0, np.conj(g) / abs(g)
+    af = abs(f)
+    d = math.hypot(af, abs(g))
+    return af / d, (f / af) * np.conj(g) / d
+
+
+def _maybe_project(Targ, factor, ax, eigA, thresholds=_default_thresholds, verbosity=0):
+    """Trefethen/Wright projection onto the invariant subspace of the eigenvalues near the window:
+    `_maybe_project(Targ, factor, ax, eigA, thresholds, verbosity) -> (Tproj, eigAproj)`  [src/compute.jl:284-361].
+    A one-time host pre-step (it stays on the host in the reference too); with the default proj_lev = Inf every
+    eigenvalue is selected and T is returned untouched (compute.jl:322-328)."""
+    Targ = np.asarray(Targ)
+    m = Targ.shape[0]
+    eigA = np.asarray(eigA)
+    axis_w, axis_h = ax[1] - ax[0], ax[3] - ax[2]
+    if factor >= 0:
+        proj_w, proj_h = axis_w * factor, axis_h * factor
+    else:
+        proj_size = -1.0 / factor
+    npick = 0
+    ew_range = list(ax)
+    selection = None
+    if m > thresholds.minnev and eigA.size:
+        while npick < thresholds.minnev:
+            if factor >= 0:
+                ew_range = [ew_range[0] - proj_w, ew_range[1] + proj_w, ew_range[2] - proj_h, ew_range[3] + proj_h]
+                selection = np.flatnonzero((eigA.real > ew_range[0]) & (eigA.real < ew_range[1])
+                                           & (eigA.imag > ew_range[2]) & (eigA.imag < ew_range[3]))
+            else:
+                selection = np.flatnonzero(np.abs(eigA) > proj_size)
+                proj_size *= 0.5
+            npick = len(selection)
+            if factor == 0:
+                break
+    else:
+        npick = m
+    if npick == m:
+        return Targ, eigA.copy()
+    if verbosity > 1:
+        print(f"projection reduces rank {m} -> {npick}")
+    eigAproj = eigA[selection]
+    Tp = np.array(Targ, dtype=np.complex128)
+    Tp = np.triu(Tp)  # UpperTriangular semantics: the strict lower part is not part of the matrix
+    for i in range(npick):
+        for k in range(selection[i] - 1, i - 1, -1):  # swap diagonal entries k, k+1 (0-based) by a Givens similarity
+            c, sn = _givens(np.conj(Tp[k, k + 1]), np.conj(Tp[k, k] - Tp[k + 1, k + 1]))
+            sn = -np.conj(sn)  # givens(f, g, k+1, k) with i1 > i2 flips the rotation (LinearAlgebra.givens)
+            # rmul!(Tproj, adjoint(G)): columns k, k+1
+            a1, a2 = Tp[:, k].copy(), Tp[:, k + 1].copy()
+            Tp[:, k] = a1 * c + a2 * np.conj(sn)
+            Tp[:, k + 1] = -a1 * sn + a2 * c
+            # lmul!(G, Tproj): rows k, k+1
+            r1, r2 = Tp[k, :].copy(), Tp[k + 1, :].copy()
+            Tp[k, :] = c * r1 + sn * r2
+            Tp[k + 1, :] = -np.conj(sn) * r1 + c * r2
+    return np.asfortranarray(np.triu(Tp[:npick, :npick])), eigAproj
+
+
 def tidyaxes(vmin, vmax, tol):
     """src/utils.jl:237-248"""
     round_to = (vmax - vmin) * tol
@@ -208,8 +271,6 @@ def psa_compute(Targ, npts, ax, eigA, opts=None, S=None, *, psatol=1e-5, thresho
     opts = dict(opts or {})
     Targ = np.asarray(Targ)
     m, n = Targ.shape
-    if opts.get("proj_lev", math.inf) != math.inf:
-        raise NotImplementedError("projection (_maybe_project) is a host pre-step outside the GPU path")
     levels = opts.get("levels")
     re_calc = opts.get("recompute_levels", levels is None)
     if levels is None:
@@ -223,8 +284,16 @@ def psa_compute(Targ, npts, ax, eigA, opts=None, S=None, *, psatol=1e-5, thresho
         rng = rng or np.random.default_rng()
         q0 = rng.standard_normal(n) + 1j * rng.standard_normal(n)
         q0 = q0 / np.linalg.norm(q0)
+    eigAproj = np.array(eigA)
+    Tproj = Targ
+    if m == n:  # compute.jl:147-153: projection only for square dense input
+        Tproj, eigAproj = _maybe_project(Targ, opts.get("proj_lev", math.inf), ax, np.asarray(eigA), thresholds,
+                                         opts.get("verbosity", 1))
+        m = n = Tproj.shape[0]
+        q0 = np.asarray(q0)[:n]
+        q0 = q0 / np.linalg.norm(q0) if len(q0) else q0
     try:
-        Z, algo, _ = psacore(Targ, S, q0, x, y, m - n + 1, tol=psatol, thresholds=thresholds, ngpus=ngpus, ctx=ctx,
+        Z, algo, _ = psacore(Tproj, S, q0, x, y, m - n + 1, tol=psatol, thresholds=thresholds, ngpus=ngpus, ctx=ctx,
                              cancel=ctrlflag)
     except PsaGpuCancelled:
         return None
@@ -236,4 +305,4 @@ def psa_compute(Targ, npts, ax, eigA, opts=None, S=None, *, psatol=1e-5, thresho
         levels, err = recalc_levels(Z, ax)
     elif np.min(levels) > math.log10(np.max(Z)) or np.max(levels) < math.log10(np.min(Z)):
         levels, err = recalc_levels(Z, ax)  # compute.jl:255-260
-    return Z, x, y, levels, err, Targ, np.array(eigA), algo
+    return Z, x, y, levels, err, Tproj, eigAproj, algo

@@ -66,13 +66,32 @@ def test_scale_equal_and_levels_match_oracle(pkg):
     assert err == erro and np.allclose(lev, levo)
 
 
+def test_maybe_project_reorders_schur_form(pkg):
+    """_maybe_project (compute.jl:284-361): unitary similarity that moves the selected eigenvalues to the top."""
+    from pseudospectra_jl_b200 import compute as hc
+    T, eigA = po.complex_schur(po.random_complex(120, 3))
+    ax = [-3.0, 3.0, -3.0, 3.0]
+    Tn, en = hc._maybe_project(T, np.inf, ax, eigA)      # default: every eigenvalue selected -> untouched
+    assert Tn is T and np.array_equal(en, eigA)
+    Tp, ep = hc._maybe_project(T, 0.5, ax, eigA)
+    k = len(ep)
+    assert 20 <= k < 120 and Tp.shape == (k, k) and np.abs(np.tril(Tp, -1)).max() == 0
+    assert np.allclose(np.diagonal(Tp), ep, atol=1e-11)  # selected eigenvalues, in their original order
+    inside = (eigA.real > -3 - 6 * 0.5) & (eigA.real < 3 + 6 * 0.5)
+    assert set(np.round(ep, 9)) <= set(np.round(eigA[inside], 9))
+    for z in (0.3 + 0.2j, -1.0 + 2.0j):                  # restriction to an invariant subspace: resolvent norm shrinks
+        assert po.sigmin_svd(Tp, z) >= po.sigmin_svd(T, z) * (1 - 1e-10)
+    Tm, em = hc._maybe_project(T, -0.2, ax, eigA)        # negative factor: keep |lambda| > 1/|factor| (halving until >= 20)
+    assert len(em) >= 20 and np.abs(em).min() > 5.0 / 2 ** 8
+    small, es = po.complex_schur(po.random_complex(15, 1))
+    assert hc._maybe_project(small, 0.1, ax, es)[0] is small  # m <= minnev: no projection
+
+
 def test_psacore_argument_errors(pkg):
     with pytest.raises(ValueError):
         pkg.psacore(np.ones((3, 5)), None, np.ones(5), [0.0], [0.0], 1)  # m < n, compute.jl:459-461
     with pytest.raises(NotImplementedError):
         pkg.psacore(np.ones((70, 70)), np.eye(70), np.ones(70), [0.0], [0.0], 1)  # generalised
-    with pytest.raises(NotImplementedError):
-        pkg.psa_compute(np.ones((70, 70)), 8, [-1, 1, -1, 1], [], {"proj_lev": 0.5})
 
 
 def _shard_worker(rank, world, port, ly, lx, out):
