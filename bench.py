@@ -353,6 +353,14 @@ def run_ours(args):
         flops_per_launch = stats_acc["flops"] / max(stats_acc["solve_launches"], 1)
         achieved = flops_per_launch / (solve_ms_avg * 1e-3) * 1e-12 if solve_ms_avg > 0 else 0.0
         pk = peak["zgemm"]["sustained_tflops"]
+        traffic, traffic_note = None, None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (profiles/)
+            nm = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_metrics.json")))
+            traffic = nm["dram_bytes_read"] + nm["dram_bytes_write"]
+            traffic_note = ("bytes per launch from one ncu --set full capture of a full-occupancy launch (%d shifts); "
+                            "algorithmic bytes for that launch: 79.7e9" % nm["shifts_in_launch"])
+        except (OSError, KeyError, ValueError):
+            pass
         out = {
             "metric": METRIC, "value": points * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -369,7 +377,8 @@ def run_ours(args):
                                         "(MEASURED_PEAKS.json holds no FP64 figure; raw DMMA issue peak 37.2)",
                          "flops_per_launch": flops_per_launch, "ms_per_launch": solve_ms_avg,
                          "solve_share_of_step": stats_acc["solve_ms"] / max(stats_acc["grid_ms"], 1e-9),
-                         "whole_step_tflops": stats_acc["flops"] / (ms_total * 1e-3) * 1e-12, "traffic": None},
+                         "whole_step_tflops": stats_acc["flops"] / (ms_total * 1e-3) * 1e-12, "traffic": traffic,
+                         "traffic_note": traffic_note},
             "lanczos": {"mean_iters": float(counts[2] / max(counts[3], 1)), "nonconverged": int(counts[0]),
                         "fallback": int(counts[1]), "ticks_per_step": stats_acc["ticks"] / args.steps},
             "schur_s": schur_s, "schur": how, "bcast_s": bcast_s, "algo": state["algo"],
