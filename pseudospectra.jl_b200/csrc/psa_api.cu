@@ -191,7 +191,7 @@ int slot_capacity(const Context* ctx, const Device& d, long long points) {
   if (ctx->algo == PSA_ALGO_HESSQR || ctx->algo == PSA_ALGO_RECT_QR) {
     cap = hess_slot_capacity(ctx->n, d.num_sms);
   } else {
-    cap = 2LL * d.num_sms * NS;  // two resident solve CTAs per SM, NS shifts each
+    cap = 4LL * d.num_sms * NS;  // four resident solve CTAs per SM, NS shifts each
   }
   long long w = std::min(cap, (points + NS - 1) / NS * NS);
   return (int)std::max<long long>(w, NS);
@@ -211,14 +211,12 @@ int set_solve_attr(Context* ctx) {
   if (ctx->solve_attr_set) return PSA_OK;
   for (auto& d : ctx->devs) {
     PSA_CUDA(cudaSetDevice(d.dev));
-    PSA_CUDA(cudaFuncSetAttribute(solve_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem(64)));
-    PSA_CUDA(cudaFuncSetAttribute(solve_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem(48)));
-    PSA_CUDA(cudaFuncSetAttribute(solve_kernel<48>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     PSA_CUDA(cudaFuncSetAttribute(solve_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem(32)));
     PSA_CUDA(cudaFuncSetAttribute(solve_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem(16)));
-    PSA_CUDA(cudaFuncSetAttribute(solve_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    PSA_CUDA(cudaFuncSetAttribute(solve_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem(8)));
     PSA_CUDA(cudaFuncSetAttribute(solve_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     PSA_CUDA(cudaFuncSetAttribute(solve_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    PSA_CUDA(cudaFuncSetAttribute(solve_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int rc = hess_set_attrs();
     if (rc != 0) {
       ctx->err = "cudaFuncSetAttribute failed for the HessQR kernels";
@@ -246,24 +244,27 @@ SolveParams solve_params(const Context* ctx, const Device& d) {
   return sp;
 }
 
-// Panel width for a tick.  Wide panels reuse each T tile for more shifts; narrow ones spread the active shifts
-// over every SM when few are active (grid tails, strong scaling over many GPUs).  The choice minimises a small
-// cost model measured on B200 (profiles/r01_panel_sweep.txt): launch time, relative to a full 64-wide launch,
-// of a CTA running alone on its SM (T1) and of two co-resident CTAs (T2); more panels than 2 per SM run in rounds.
+// Panel width for a tick.  The solve kernel runs 4-warp CTAs (one warp per SM sub-partition), up to 4 per SM, each
+// owning a panel of 32, 16 or 8 shifts.  Wide panels reuse each T tile for more shifts; narrow ones spread the
+// active shifts over every SM when few are active (grid tails, strong scaling over many GPUs).  The choice
+// minimises a small cost model measured on B200 (profiles/r01_panel_sweep.txt): launch time, relative to a full
+// launch, with k = 1..4 co-resident CTAs per SM; more panels than that run in rounds.
 int pick_panel_width(int n_active, int num_sms) {
   const char* env = getenv("PSA_PANEL_WIDTH");  // experiments only
   const int forced = env ? atoi(env) : 0;
-  if (forced == 64 || forced == 48 || forced == 32 || forced == 16) return forced;
-  static const int widths[4] = {16, 32, 48, 64};
-  static const double t1[4] = {0.205, 0.319, 0.440, 0.560}, t2[4] = {0.308, 0.537, 0.770, 1.0};
-  int best = 64;
+  if (forced == 32 || forced == 16 || forced == 8) return forced;
+  static const int widths[3] = {8, 16, 32};
+  static const double cost[3][5] = {{0.0, 0.154, 0.170, 0.231, 0.291},   // width 8:  k = 1..4 CTAs per SM
+                                    {0.0, 0.214, 0.271, 0.410, 0.519},   // width 16
+                                    {0.0, 0.360, 0.515, 0.779, 1.000}};  // width 32
+  int best = 32;
   double best_cost = 1e300;
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 3; ++i) {
     const int panels = (n_active + widths[i] - 1) / widths[i];
     const int per_sm = (panels + num_sms - 1) / num_sms;  // CTAs on the busiest SM
-    const double cost = (per_sm / 2) * t2[i] + (per_sm % 2) * t1[i];
-    if (cost < best_cost - 1e-12) {
-      best_cost = cost;
+    const double c = (per_sm / 4) * cost[i][4] + cost[i][per_sm % 4];
+    if (c < best_cost - 1e-12) {
+      best_cost = c;
       best = widths[i];
     }
   }
@@ -274,10 +275,9 @@ void launch_solve(const Context* ctx, const Device& d, int n_active, int width) 
   const SolveParams sp = solve_params(ctx, d);
   const int panels = (n_active + width - 1) / width;
   switch (width) {
-    case 64: solve_kernel<64><<<panels, SOLVE_THREADS, solve_smem(64), d.stream>>>(sp); break;
-    case 48: solve_kernel<48><<<panels, SOLVE_THREADS, solve_smem(48), d.stream>>>(sp); break;
     case 32: solve_kernel<32><<<panels, SOLVE_THREADS, solve_smem(32), d.stream>>>(sp); break;
-    default: solve_kernel<16><<<panels, SOLVE_THREADS, solve_smem(16), d.stream>>>(sp); break;
+    case 16: solve_kernel<16><<<panels, SOLVE_THREADS, solve_smem(16), d.stream>>>(sp); break;
+    default: solve_kernel<8><<<panels, SOLVE_THREADS, solve_smem(8), d.stream>>>(sp); break;
   }
 }
 

@@ -13,15 +13,15 @@ namespace psa {
 // ---- tiling constants -------------------------------------------------------------------------------
 constexpr int MB = 64;                        // rows per block row (M tile)
 constexpr int KC = 16;                        // contraction chunk (one pipeline step)
-constexpr int NS = 64;                        // widest panel (shifts per CTA)
+constexpr int NS = 32;                        // widest panel (shifts per CTA)
 constexpr int APAD = 384;                     // active lists are padded to a multiple of lcm(16,32,48,64,96,128)
 constexpr int CPB = MB / KC;                  // chunks per block = 4
 constexpr int TILE_ELEMS = MB * KC;           // complex elements per packed T tile
 constexpr int TILE_BYTES = TILE_ELEMS * 16;   // 16 KiB
 constexpr int XROW_BYTES = KC * 16 + 64;      // 320: X smem row stride (64 B pad -> conflict-free B-fragment loads)
-constexpr int STAGES = 3;                     // <= 4 (producer/consumer distance rule)
-constexpr int SOLVE_THREADS = 256;
-// per panel width NSV (64, 32 or 16 shifts per CTA): X tile NSV rows, ring of STAGES (T tile + X tile) stages,
+constexpr int STAGES = 2;                     // <= 4 (producer/consumer distance rule)
+constexpr int SOLVE_THREADS = 128;            // 4 warps: one per SM sub-partition, each owning 16 rows x all shifts
+// per panel width NSV (32, 16 or 8 shifts per CTA): X tile NSV rows, ring of STAGES (T tile + X tile) stages,
 // then mbarriers (64 B reserved) + shifts + 2 pointer tables
 __host__ __device__ constexpr int stage_bytes(int nsv) { return TILE_BYTES + nsv * XROW_BYTES; }
 __host__ __device__ constexpr int solve_smem(int nsv) { return STAGES * stage_bytes(nsv) + 64 + nsv * 16 + nsv * 8 * 2; }
@@ -140,15 +140,17 @@ struct StepCursor {
   }
 };
 
-// One CTA = one panel of NSV shifts (64 in steady state; 32 / 16 when few shifts are active, so that the
-// panels still cover every SM); 8 warps arranged 4 (M) x 2 (N): warp tile 16 rows x NSV/2 shifts.
+// One CTA = one panel of NSV shifts (32 in steady state; 16 / 8 when few shifts are active, so that the panels
+// still cover every SM); 4 warps, one per SM sub-partition, warp w owning rows 16w..16w+15 of the block row for all
+// NSV shifts; up to 4 CTAs per SM, i.e. four independent barrier domains whose pipeline bubbles overlap
+// (measured: 33.0 TFLOP/s against 31.9 for the earlier 8-warp / 64-shift CTAs, profiles/r01_panel_sweep.txt).
 // Left-looking block forward substitution (both phases, see pack_kernel): for block row I
 //   acc = sum_{c < 4I} L[I][c] * X[c]              (GEMM steps: T tile + X tile through the bulk-copy ring)
 //   for cp = 0..3: rows 16cp..16cp+15:  x = (L_dd - z)^{-1} (rhs - acc)   (diag step, per-shift, in registers)
 //                  acc += L[I][4I+cp] * x           (rows below, same DMMA code)
 template <int NSV>
-__global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_kernel(SolveParams P) {
-  constexpr int SW = NSV / 2;  // shifts per warp
+__global__ void __launch_bounds__(SOLVE_THREADS, 4) solve_kernel(SolveParams P) {
+  constexpr int SW = NSV;      // shifts per warp: every warp sees the whole panel
   constexpr int NT = SW / 8;   // 8-wide DMMA column tiles per warp
   constexpr int STAGE_BYTES = stage_bytes(NSV);
   extern __shared__ __align__(128) unsigned char smem[];
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_kernel(SolveParams P) 
   const double2** qptr = (const double2**)(wptr + NSV);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wm = warp >> 1, wn = warp & 1;  // the 2 warps sharing a row group sit on different SM sub-partitions
+  const int wm = warp, wn = 0;  // warp = row group = SM sub-partition
 
   if (tid < NSV) {
     const int slot = P.active[panel * NSV + tid];

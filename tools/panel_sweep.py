@@ -6,13 +6,13 @@ import numpy as np
 import psa_b200_loader
 P = psa_b200_loader.load_package()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
-WIDTHS = (64, 48, 32, 16)
+WIDTHS = (32, 16, 8)
 rng = np.random.default_rng(0)
 T = np.triu(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n) + np.diag(3 * rng.standard_normal(n))
 g = P.PsaGpu(1)
 g.set_matrix(T)
 print("n", n)
-for ns in (18944, 9472, 4736, 2368, 1184, 592, 148):
+for ns in (18944, 14208, 9472, 7104, 4736, 3552, 2368, 1184, 592, 148):
     z = 5 * (rng.standard_normal(ns) + 1j * rng.standard_normal(ns))
     Q = rng.standard_normal((ns, n)) + 1j * rng.standard_normal((ns, n))
     for w in WIDTHS:
