@@ -254,9 +254,9 @@ int pick_panel_width(int n_active, int num_sms) {
   const int forced = env ? atoi(env) : 0;
   if (forced == 32 || forced == 16 || forced == 8) return forced;
   static const int widths[3] = {8, 16, 32};
-  static const double cost[3][5] = {{0.0, 0.154, 0.170, 0.231, 0.291},   // width 8:  k = 1..4 CTAs per SM
-                                    {0.0, 0.214, 0.271, 0.410, 0.519},   // width 16
-                                    {0.0, 0.360, 0.515, 0.779, 1.000}};  // width 32
+  static const double cost[3][5] = {{0.0, 0.131, 0.162, 0.223, 0.280},   // width 8:  k = 1..4 CTAs per SM
+                                    {0.0, 0.207, 0.290, 0.406, 0.519},   // width 16
+                                    {0.0, 0.349, 0.509, 0.772, 1.000}};  // width 32
   int best = 32;
   double best_cost = 1e300;
   for (int i = 0; i < 3; ++i) {

@@ -258,90 +258,127 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 4) solve_kernel(SolveParams P) 
     advance_prod();
   }
 
+  // optional per-phase cycle counters (build with -DPSA_TIMING; prints from the first and last CTA)
+#ifdef PSA_TIMING
+  long long tm_wait = 0, tm_gemm = 0, tm_diag = 0, tm_sync = 0, tm0;
+#define PSA_T0() tm0 = clock64()
+#define PSA_T1(acc) acc += clock64() - tm0
+#else
+#define PSA_T0()
+#define PSA_T1(acc)
+#endif
   for (int t = 0; t < total_steps; ++t) {
     const int stage = t % STAGES;
     const uint32_t parity = (uint32_t)(t / STAGES) & 1u;
     unsigned char* sb = smem + stage * STAGE_BYTES;
     const int flip = cons.phase ? (KC - 1) : 0;
+    PSA_T0();
     mbar_wait(&full_bar[stage], parity);
+    PSA_T1(tm_wait);
 
     if (cons.c < CPB * cons.I) {
+      PSA_T0();
       gemm_step(sb, flip);
+      PSA_T1(tm_gemm);
     } else {
+      PSA_T0();
       const int cp = cons.c - CPB * cons.I;  // diagonal sub-chunk 0..3
+      unsigned char* Xt = sb + TILE_BYTES;
       if (wm == cp) {
-        // this warp owns rows 16cp..16cp+15 of the block row for its SW shifts: finish them (lane = shift).
-        const bool solver = lane < SW;
-        const int s = SW * wn + (solver ? lane : 0);
-        const int mem0 = cons.phase ? n_pad - KC * cons.c - KC : KC * cons.c;
-        const double2* rp = (cons.phase ? (const double2*)wptr[s] : qptr[s]) + mem0;
-        double2 b[KC];  // indexed by processing row r; memory / smem position is r ^ flip
-#pragma unroll
-        for (int r = 0; r < KC; ++r) b[r] = rp[r ^ flip];
-        unsigned char* Xt = sb + TILE_BYTES;
-        // transpose the accumulators through smem: element (row r, shift sl) -> Xt[sl][r ^ flip]
+        // this warp owns rows 16cp..16cp+15 of the block row: hand its accumulators over through the stage's
+        // (unused) X buffer, transposed: element (row r, shift sl) -> Xt[sl][r ^ flip]
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int r = 8 * mt + (lane >> 2), sl = SW * wn + 8 * nt + 2 * (lane & 3) + e;
+              const int r = 8 * mt + (lane >> 2), sl = 8 * nt + 2 * (lane & 3) + e;
               *reinterpret_cast<double2*>(Xt + sl * XROW_BYTES + ((r ^ flip) << 4)) =
                   make_double2(cre[mt][nt][e], cim[mt][nt][e]);
               cre[mt][nt][e] = 0.0;
               cim[mt][nt][e] = 0.0;
             }
-        __syncwarp();
+      }
+      __syncthreads();
+      // Per-shift 16x16 triangular solve (L_dd - z~ I) x = rhs - acc, spread over the whole CTA: four lanes per
+      // shift (lane p owns rows p, p+4, p+8, p+12), pivots broadcast with shuffles.  The FP64 pipe is saturated by
+      // the co-resident CTAs' DMMAs, so what matters here is the number of FP64 instructions per thread.
+      {
+        constexpr int GROUPS = SOLVE_THREADS / 4;          // shifts solved concurrently (32)
+        const int grp = tid >> 2, pl = lane & 3;            // shift group and lane-in-group
+        const bool solver = grp < NSV;
+        const int s = solver ? grp : 0;
+        static_assert(NSV <= GROUPS, "one 4-lane group per shift");
+        const int mem0 = cons.phase ? n_pad - KC * cons.c - KC : KC * cons.c;
+        const double2* rp = (cons.phase ? (const double2*)wptr[s] : qptr[s]) + mem0;
         double2* xrow = reinterpret_cast<double2*>(Xt + s * XROW_BYTES);
-#pragma unroll
-        for (int r = 0; r < KC; ++r) {
-          const double2 a = xrow[r ^ flip];
-          b[r].x -= a.x;
-          b[r].y -= a.y;
-        }
         const double2* At = reinterpret_cast<const double2*>(sb);
         double2 zt = zsh[s];
         if (cons.phase == 0) zt.y = -zt.y;  // adjoint system: diagonal conj(t_ii - z)
         const int p0 = MB * cons.I + KC * cp;
+        double2 b[4], dinv[4];
 #pragma unroll
-        for (int r = 0; r < KC; ++r) {  // forward substitution in processing order
-          const int m = KC * cp + r;
+        for (int i = 0; i < 4; ++i) {
+          const int r = 4 * i + pl, m = KC * cp + r;
+          const double2 g = rp[r ^ flip], a = xrow[r ^ flip];
+          b[i] = make_double2(g.x - a.x, g.y - a.y);
           double2 d = At[((r >> 2) * 8 + (m >> 3)) * 32 + (m & 7) * 4 + (r & 3)];
           d.x -= zt.x;
           d.y -= zt.y;
-          double2 x = cmul(b[r], crecip(d));
+          const double inv = __drcp_rn(fma(d.x, d.x, d.y * d.y));
+          dinv[i] = make_double2(d.x * inv, -d.y * inv);
+        }
+#pragma unroll
+        for (int r = 0; r < KC; ++r) {  // forward substitution in processing order; pivot r lives on lane r & 3
+          const int ir = r >> 2, pr = r & 3;
+          double2 x = cmul(b[ir], dinv[ir]);
           const int op = cons.phase ? n_pad - 1 - (p0 + r) : p0 + r;
           if (op >= n) x = make_double2(0.0, 0.0);
-          b[r] = x;
+          if (pl == pr) b[ir] = x;
+          const int src = (lane & ~3) | pr;
+          x.x = __shfl_sync(0xffffffffu, x.x, src);
+          x.y = __shfl_sync(0xffffffffu, x.y, src);
 #pragma unroll
-          for (int r2 = r + 1; r2 < KC; ++r2) {
-            const int m2 = KC * cp + r2;
-            const double2 l = At[((r >> 2) * 8 + (m2 >> 3)) * 32 + (m2 & 7) * 4 + (r & 3)];
-            cmsub(b[r2], l, x);
+          for (int i = ir; i < 4; ++i) {
+            const int r2 = 4 * i + pl;  // this lane's row in group i
+            if (r2 > r) {
+              const int m2 = KC * cp + r2;
+              const double2 l = At[((r >> 2) * 8 + (m2 >> 3)) * 32 + (m2 & 7) * 4 + (r & 3)];
+              cmsub(b[i], l, x);
+            }
           }
         }
-        double2* op_ = wptr[s] + mem0;
         if (solver) {
+          double2* op_ = wptr[s] + mem0;
 #pragma unroll
-          for (int r = 0; r < KC; ++r) {
-            xrow[r ^ flip] = b[r];
-            op_[r ^ flip] = b[r];
+          for (int i = 0; i < 4; ++i) {
+            const int r = 4 * i + pl;
+            xrow[r ^ flip] = b[i];
+            op_[r ^ flip] = b[i];
           }
         }
         fence_proxy_async();  // belt and braces: later block rows re-read these x with asynchronous copies
       }
       __syncthreads();
       if (wm > cp) gemm_step(sb, flip);
+      PSA_T1(tm_diag);
     }
+    PSA_T0();
     __syncthreads();  // every warp is done with this stage: refill it
     if (t + STAGES < total_steps) {
       issue(prod, stage);
       advance_prod();
     }
+    PSA_T1(tm_sync);  // BAR.SYNC is deferred-blocking: the wait shows up at the first dependent instruction
     cons.advance();
     if (cons.I == nblk) cons = StepCursor{1, 0, 0};
   }
+#ifdef PSA_TIMING
+  if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+    printf("[timing] cta %d warp %d: load-wait %lld gemm %lld diag %lld barrier+issue %lld clk, %d steps\n", (int)blockIdx.x, warp,
+           tm_wait, tm_gemm, tm_diag, tm_sync, total_steps);
+#endif
 }
 
 // ---- scheduler: refill idle slots from the point queue, compact the active list -------------------------
