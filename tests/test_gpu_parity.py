@@ -97,6 +97,22 @@ def test_real_matrix_mirror_through_psa_compute(pkg, golden):
     assert Z.min() >= 10 * math.sqrt(np.finfo(float).tiny)
 
 
+def test_projection_option_through_psa_compute(pkg):
+    """opts[:proj_lev] (compute.jl:116,147-153): the host-side Schur reordering shrinks T, the GPU path then runs on
+    the projected matrix; compared with the oracle's Lanczos on the same projected T."""
+    from pseudospectra_jl_b200 import compute as hc
+    T, eigA = po.complex_schur(po.random_complex(200, 6))
+    ax = [-4.0, 4.0, -4.0, 4.0]
+    q0 = po.start_vector(200, 0)
+    out = pkg.psa_compute(T, 12, ax, eigA, {"proj_lev": 1.0}, q0=q0)
+    Z, x, y, levels, err, Tproj, eigAproj, algo = out
+    k = Tproj.shape[0]
+    assert 55 <= k < 200 and len(eigAproj) == k and algo == "sq_lanc"
+    qk = q0[:k] / np.linalg.norm(q0[:k])
+    Zc, _, _ = co.grid(Tproj, x, y, qk, nthreads=4)
+    assert _rel(Z, np.clip(Zc, po.PS_TINY, np.inf), _floor(Tproj)) < RTOL
+
+
 def test_hessqr_golden_medrect(gpu, golden):
     """test/medrect.jl: grcar(210)[:,1:end-1] -> :HessQR."""
     g = golden("hessqr210")
