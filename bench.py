@@ -21,9 +21,13 @@ import time
 
 # torchrun exports OMP_NUM_THREADS=1 to every worker.  Rank 0 performs the one-time host Schur reduction and must
 # use the host's cores for it; this has to be set before numpy/scipy load their BLAS.
+# A FIXED thread count (16, or fewer on a smaller host) keeps the BLAS-3 blocking inside zgees -- and with it the
+# rounding, hence the particular Schur basis -- identical on boxes with different core counts, so every N runs the
+# same T (a different but equally valid Schur form changes the Lanczos iteration counts by a few percent).
 _RANK0 = int(os.environ.get("RANK", "0")) == 0
+SCHUR_THREADS = min(16, os.cpu_count() or 1)
 for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
-    os.environ[_v] = str((os.cpu_count() or 1) if _RANK0 else 1)
+    os.environ[_v] = str(SCHUR_THREADS if _RANK0 else 1)
 
 import numpy as np
 
@@ -55,7 +59,7 @@ def build_workload(n: int, npts: int, seed: int = 1):
         A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
         try:  # torchrun exports OMP_NUM_THREADS=1; the one-time host reduction should use the host's cores
             from threadpoolctl import threadpool_limits
-            with threadpool_limits(limits=os.cpu_count()):
+            with threadpool_limits(limits=SCHUR_THREADS):
                 T, _ = sla.schur(A, output="complex")
         except ImportError:
             T, _ = sla.schur(A, output="complex")
