@@ -848,7 +848,15 @@ int psa_gpu_apply_resolvent(void* vctx, const double* z, int ns, const double* Q
   if (rc) return rc;
   const int W = (ns + APAD - 1) / APAD * APAD;  // padded active list
   if ((rc = ensure_slots(ctx, d, std::max(W, d.W)))) return rc;
-  double2 *dQ = nullptr, *dz = nullptr, *dV = nullptr;
+  struct Scratch {  // temporary device buffers, released on every exit path
+    double2 *Q = nullptr, *z = nullptr, *V = nullptr;
+    ~Scratch() {
+      cudaFree(Q);
+      cudaFree(z);
+      cudaFree(V);
+    }
+  } tmp;
+  double2 *&dQ = tmp.Q, *&dz = tmp.z, *&dV = tmp.V;
   const size_t n = ctx->n;
   if ((rc = dev_alloc(ctx, &dQ, ns * n))) return rc;
   if ((rc = dev_alloc(ctx, &dz, (size_t)ns))) return rc;
@@ -872,9 +880,6 @@ int psa_gpu_apply_resolvent(void* vctx, const double* z, int ns, const double* Q
     ctx->stats[PSA_STAT_SOLVE_LAUNCHES] = 1;
     ctx->stats[PSA_STAT_FLOPS] = 8.0 * (double)n * (double)n * ns;
   }
-  cudaFree(dQ);
-  cudaFree(dz);
-  cudaFree(dV);
   return PSA_OK;
 }
 
