@@ -14,7 +14,7 @@ namespace psa {
 constexpr int MB = 64;                        // rows per block row (M tile)
 constexpr int KC = 16;                        // contraction chunk (one pipeline step)
 constexpr int NS = 32;                        // widest panel (shifts per CTA)
-constexpr int APAD = 384;                     // active lists are padded to a multiple of lcm(16,32,48,64,96,128)
+constexpr int APAD = 32;                      // active lists are padded to a multiple of every panel width (8, 16, 32)
 constexpr int CPB = MB / KC;                  // chunks per block = 4
 constexpr int TILE_ELEMS = MB * KC;           // complex elements per packed T tile
 constexpr int TILE_BYTES = TILE_ELEMS * 16;   // 16 KiB
@@ -25,7 +25,7 @@ constexpr int SOLVE_THREADS = 128;            // 4 warps: one per SM sub-partiti
 // then mbarriers (64 B reserved) + shifts + 2 pointer tables
 __host__ __device__ constexpr int stage_bytes(int nsv) { return TILE_BYTES + nsv * XROW_BYTES; }
 __host__ __device__ constexpr int solve_smem(int nsv) { return STAGES * stage_bytes(nsv) + 64 + nsv * 16 + nsv * 8 * 2; }
-static_assert(2 * STAGES * 8 <= 64, "mbarrier block");
+static_assert(STAGES * 8 <= 64, "mbarrier block");
 constexpr int HIST = 128;                     // per-slot alpha/beta history stride (maxit <= 126)
 
 __host__ __device__ inline long long tiles_per_phase(int nblk) { return 2LL * nblk * (nblk + 1); }
@@ -121,7 +121,7 @@ struct SolveParams {
   const double2* packA;
   const double2* packB;
   int n, n_pad, nblk;
-  const int* active;   // slot ids, padded to a multiple of NS with the scratch slot
+  const int* active;   // slot ids, padded to a multiple of APAD with the scratch slot
   const int* n_active; // device scalar
   double2* Q0;         // [W+1][n_pad]
   double2* Q1;
@@ -396,7 +396,7 @@ struct SchedParams {
   double* slot_beta;
   double* slot_sigold;
   int* slot_sel;
-  int* active;        // out, padded with W to a multiple of NS
+  int* active;        // out, padded with W (the scratch slot) to a multiple of APAD
   int* fresh;         // out, list of newly filled slots
   int* state;         // [0]=next_point [1]=n_active [2]=n_fresh  (device)
   int* host_state;    // mapped pinned mirror
