@@ -235,6 +235,27 @@ def test_rect_qr_small_hessenberg(gpu):
     assert algo == "rect_qr" == algo_o and _rel(Z, Zo, _floor(H)) < RTOL
 
 
+def test_plain_c_driver_matches_oracle(pkg, tmp_path):
+    """The C ABI driven from plain C (tests/abi_driver.c), the way a ccall host uses it."""
+    import subprocess
+    from test_host import _build_abi_driver
+    n, lx, ly = 96, 4, 3
+    r = subprocess.run([_build_abi_driver(pkg, tmp_path), str(n), str(lx), str(ly)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    T = np.where(i < j, 0.3 * np.sin(1.0 + i + 2.0 * j) + 0.3j * np.cos(2.0 + 3.0 * i + j), 0)
+    T = T + np.diag(0.05 * np.arange(n) - 1.0 + 0.02j * np.arange(n))
+    x = np.array([-2.0 + 4.0 * k / (lx - 1) for k in range(lx)])
+    y = np.array([-1.0 + 3.0 * jj / (ly - 1) for jj in range(ly)])
+    q0 = np.cos(0.7 * np.arange(n)) + 1j * np.sin(1.3 * np.arange(n) + 0.2)
+    q0 = q0 / np.linalg.norm(q0)
+    Zc, itc, _ = co.grid(T, x, y, q0)
+    lines = [l.split() for l in r.stdout.splitlines() if l.startswith("Z ")]
+    assert len(lines) == lx * ly and r.stdout.startswith("algo 1 ")
+    for _, jj, kk, val, its in lines:
+        assert abs(float(val) - Zc[int(jj), int(kk)]) <= RTOL * Zc[int(jj), int(kk)] and int(its) == itc[int(jj), int(kk)]
+
+
 def test_unsupported_shapes_raise(pkg, gpu):
     A = np.ones((190, 189))
     with pytest.raises(pkg.PsaGpuUnsupported):

@@ -24,6 +24,23 @@ def test_abi_exports_every_declared_symbol(pkg):
     assert b"sm_100a" in ctypes.cast(lib.psa_gpu_version, ctypes.CFUNCTYPE(ctypes.c_char_p))()
 
 
+def _build_abi_driver(pkg, tmp_path):
+    import subprocess
+    exe = str(tmp_path / "abi_driver")
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    subprocess.check_call(["gcc", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "abi_driver.c"),
+                           "-o", exe, "-L", libdir, "-lpsagpu", "-lm", "-Wl,-rpath," + libdir])
+    return exe
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device exit of the plain-C driver")
+def test_plain_c_driver_links_and_fails_loudly_without_gpu(pkg, tmp_path):
+    """A C program that only includes include/psa_gpu.h links against libpsagpu.so (no Python, no torch)."""
+    import subprocess
+    r = subprocess.run([_build_abi_driver(pkg, tmp_path), "64", "3", "2"], capture_output=True, text=True)
+    assert r.returncode == 10 and "no usable sm_100" in r.stdout
+
+
 def test_strerror_and_argument_errors_without_gpu(pkg):
     lib = pkg.load_library()
     assert lib.psa_gpu_strerror(0) == b"ok"
