@@ -402,6 +402,38 @@ def psa_compute(T: np.ndarray, npts: int, ax, eigA, opts: dict | None = None, *,
     return Z, x, y, levels, err, T, np.array(eigA), algo
 
 
+def psmode_inv_lanczos(A: np.ndarray, q0: np.ndarray, z: complex, tol: float, num_its: int):
+    """Pseudomode by inverse Lanczos for upper-triangular A, n >= 200 branch.  src/modes.jl:201-261
+    (`v = T1 \\ (T2 \\ q) - beta*qold` at 229, Ritz vector `Q[:,1:end-1] * E.vectors[:,end]` at 257)."""
+    n = A.shape[0]
+    T1 = np.asfortranarray(np.triu(np.asarray(A, dtype=np.complex128)))
+    T1[np.arange(n), np.arange(n)] -= z
+    q = np.asarray(q0, dtype=np.complex128).copy()
+    qold = np.zeros(n, dtype=np.complex128)
+    Q = [q.copy()]
+    H = np.zeros((num_its + 1, num_its + 1))
+    beta = sigold = 0.0
+    sigma, l = None, 0
+    for _ in range(num_its):
+        l += 1
+        w = _blas.ztrsv(T1, q, lower=0, trans=2, diag=0)
+        v = _blas.ztrsv(T1, w, lower=0, trans=0, diag=0) - beta * qold
+        alpha = float(np.real(np.vdot(q, v)))
+        v = v - alpha * q
+        beta = float(np.linalg.norm(v))
+        qold = q
+        q = v / beta
+        Q.append(q.copy())
+        H[l, l - 1] = H[l - 1, l] = beta
+        H[l - 1, l - 1] = alpha
+        sigma = float(np.max(sla.eigvalsh(H[:l, :l])))
+        if abs(sigold / sigma - 1) < tol or beta == 0:
+            break
+        sigold = sigma
+    _, vecs = sla.eigh(H[:l, :l])
+    return 1.0 / math.sqrt(sigma), np.column_stack(Q[:l]) @ vecs[:, -1], l
+
+
 def sigmin_svd(T: np.ndarray, z: complex) -> float:
     """Independent checker: smallest singular value of (T - zI) (same quantity as compute.jl:510-518)."""
     m, n = T.shape

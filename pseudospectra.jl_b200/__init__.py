@@ -3,4 +3,4 @@ interface.  The directory name contains a dot, so import it through `psa_b200_lo
 repository root (tests, bench.py and __graft_entry__.py all do)."""
 from ._lib import (PsaGpu, PsaGpuCancelled, PsaGpuError, PsaGpuUnsupported, load as load_library, version,  # noqa: F401
                    EXPORTS, LIB_PATH)
-from .compute import ComputeThresholds, psa_compute, psacore, vec2ax  # noqa: F401
+from .compute import ComputeThresholds, psa_compute, psacore, psmode_inv_lanczos, vec2ax  # noqa: F401

@@ -237,6 +237,72 @@ def _maybe_project(Targ, factor, ax, eigA, thresholds=_default_thresholds, verbo
     return np.asfortranarray(np.triu(Tp[:npick, :npick])), eigAproj
 
 
+def psmode_inv_lanczos(A, q0, z, tol, num_its, *, fallbacksvd=False, ctx: PsaGpu | None = None, resident=False):
+    """psmode_inv_lanczos(A,q,z,tol,num_its) -> Z,q          [src/modes.jl:185-274]
+
+    Pseudomode at one point z: the same inverse-Lanczos recurrence as `_psa_lanczos!`, but the Lanczos basis is kept
+    and the right singular vector for sigma_min(zI - A) is assembled from the Ritz vector (modes.jl:255-260).
+    The operator application v = T1^-1 (T2^-1 q), T2 = T1' (modes.jl:229) runs on the GPU through the solve kernel
+    (`psa_gpu_apply_resolvent`, one shift); A must be upper triangular (the Schur factor, as `modeplot` passes it).
+    n < 200 uses a plain host SVD exactly like the reference (modes.jl:193-200).  Returns (nan, nan) when the
+    iteration does not converge and fallbacksvd is False (modes.jl:262-272)."""
+    A = np.asarray(A)
+    m, n = A.shape
+    if m != n:
+        raise ValueError("Matrix must be square")  # modes.jl:188
+    z = complex(z)
+    q = np.asarray(q0, dtype=np.complex128).copy()
+    if n < 200:
+        A1 = np.array(A, dtype=np.complex128)
+        A1[np.arange(n), np.arange(n)] -= z
+        U, S, Vh = np.linalg.svd(A1)
+        return float(S[-1]), Vh[-1].conj()
+    if ctx is None:
+        ctx = _context(1)
+    if not (resident and ctx.shape == (n, n)):
+        ctx.set_matrix(A)
+    H = np.zeros((num_its + 1, num_its + 1))
+    qold = np.zeros(n, dtype=np.complex128)
+    Q = [q.copy()]
+    beta, sigold, sigma, l = 0.0, 0.0, None, 0
+    for _ in range(num_its):
+        l += 1
+        v = ctx.apply_resolvent(np.array([z]), q[None, :])[0] - beta * qold
+        alpha = float(np.real(np.vdot(q, v)))
+        v = v - alpha * q
+        beta = float(np.linalg.norm(v))
+        qold = q
+        with np.errstate(all="ignore"):
+            q = v / beta
+        Q.append(q.copy())
+        H[l, l - 1] = H[l - 1, l] = beta
+        H[l - 1, l - 1] = alpha
+        try:
+            sigma = float(np.max(np.linalg.eigvalsh(H[:l, :l])))
+        except np.linalg.LinAlgError:
+            sigma = 1e308
+        with np.errstate(all="ignore"):
+            resid = abs(sigold / sigma - 1)
+        if resid < tol or beta == 0:
+            break
+        sigold = sigma
+    Z = 1.0 / math.sqrt(sigma)
+    try:
+        _, vecs = np.linalg.eigh(H[:l, :l])
+        qv = np.column_stack(Q[:l]) @ vecs[:, -1]
+    except np.linalg.LinAlgError:
+        l = num_its
+        qv = None
+    if l >= num_its:
+        if fallbacksvd:
+            A1 = np.triu(np.array(A, dtype=np.complex128))
+            A1[np.arange(n), np.arange(n)] -= z
+            U, S, Vh = np.linalg.svd(A1)
+            return float(S[-1]), Vh[-1].conj()
+        return float("nan"), float("nan")
+    return Z, qv
+
+
 def tidyaxes(vmin, vmax, tol):
     """src/utils.jl:237-248"""
     round_to = (vmax - vmin) * tol

@@ -256,6 +256,24 @@ def test_plain_c_driver_matches_oracle(pkg, tmp_path):
         assert abs(float(val) - Zc[int(jj), int(kk)]) <= RTOL * Zc[int(jj), int(kk)] and int(its) == itc[int(jj), int(kk)]
 
 
+def test_pseudomode_inverse_lanczos(pkg):
+    """psmode_inv_lanczos (modes.jl:185-274): sigma_min and the pseudomode at one point, with the
+    operator applications on the GPU; compared with the oracle's restatement and with the defining residual."""
+    T, eigA = po.complex_schur(po.random_complex(320, 9))
+    q0 = po.start_vector(320, 4)
+    for z in (2.0 + 1.5j, -25.0 + 3.0j):
+        Zg, qg = pkg.psmode_inv_lanczos(T, q0, z, 1e-10, 60)
+        Zo, qo, l = po.psmode_inv_lanczos(T, q0, z, 1e-10, 60)
+        assert abs(Zg - Zo) <= 1e-8 * Zo
+        ph = np.vdot(qo, qg) / abs(np.vdot(qo, qg))
+        assert np.linalg.norm(qg - ph * qo) <= 1e-6 * np.linalg.norm(qo)
+        s = po.sigmin_svd(T, z)
+        assert abs(Zg - s) <= 1e-6 * s
+        assert abs(np.linalg.norm((T - z * np.eye(320)) @ qg) / np.linalg.norm(qg) - s) <= 1e-4 * s
+    Zs, qs = pkg.psmode_inv_lanczos(T[:150, :150], q0[:150], 1.0 + 1.0j, 1e-8, 30)  # n < 200: host SVD (modes.jl:193)
+    assert abs(Zs - po.sigmin_svd(T[:150, :150], 1.0 + 1.0j)) <= 1e-12 * Zs
+
+
 def test_unsupported_shapes_raise(pkg, gpu):
     A = np.ones((190, 189))
     with pytest.raises(pkg.PsaGpuUnsupported):
