@@ -100,7 +100,6 @@ def test_real_matrix_mirror_through_psa_compute(pkg, golden):
 def test_projection_option_through_psa_compute(pkg):
     """opts[:proj_lev] (compute.jl:116,147-153): the host-side Schur reordering shrinks T, the GPU path then runs on
     the projected matrix; compared with the oracle's Lanczos on the same projected T."""
-    from pseudospectra_jl_b200 import compute as hc
     T, eigA = po.complex_schur(po.random_complex(200, 6))
     ax = [-4.0, 4.0, -4.0, 4.0]
     q0 = po.start_vector(200, 0)
