@@ -84,7 +84,8 @@ int psa_gpu_set_matrix_device(void* ctx, const double* d_T, int64_t ldt, int m, 
  * (T-z)^{-1}(T-z)^{-H} by the inverse-Lanczos recurrence of `_psa_lanczos!` (compute.jl:619-665) started from
  * q0 (unit norm, length >= n; the same vector for every point, compute.jl:207-210,622) and returns
  * Z[j + k*ly] = 1/sqrt(sigma) (compute.jl:611), column-major ly x lx.
- *   tol, maxit, bigsigma : psatol (1e-5), thresholds.maxit_lancs (99), 0.1*floatmax (compute.jl:88,27,475)
+ *   tol, maxit, bigsigma : psatol (1e-5), thresholds.maxit_lancs (99), 0.1*floatmax (compute.jl:88,27,475);
+ *                          maxit above 126 is clamped to 126 (size of the per-shift alpha/beta history)
  *   iters  : nullable, ly x lx int32, Lanczos iterations per point
  *   counts : nullable, PSA_NCOUNTS int64 (see PSA_COUNT_*)
  *   cancel : nullable; polled between scheduler ticks; *cancel == 1 -> PSA_ERR_CANCELLED (compute.jl:202-204)
