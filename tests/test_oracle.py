@@ -124,3 +124,54 @@ def test_recalc_levels_basic():
     assert err == 0 and len(lev) >= 2 and np.all(np.diff(lev) > 0) and lev[-1] <= np.log10(0.03 * 2) + 1e-9
     lev, err = po.recalc_levels(np.full((3, 3), 1e-200), [-1, 1, -1, 1])
     assert err == -2
+
+
+@pytest.mark.parametrize("name", ["grcar", "toeplitz", "random"])
+def test_oracle_no_worse_than_tolerance_vs_svd_across_matrix_classes(name):
+    """Pins the oracle (both restatements) against dense svdvals on sampled points for the BASELINE matrix families;
+    the Lanczos stopping rule (tol 1e-5 on sigma = 1/sigma_min^2) bounds the error wherever sigma_min is above the
+    rounding floor n*eps*||T||."""
+    if name == "grcar":
+        A = po.grcar(80)
+    elif name == "toeplitz":
+        A = po.toeplitz_from_symbol([0.0, 1.0], [0.0, 0.0, 0.25], 90)  # examples/toeplitz.jl 'triangle'
+    else:
+        A = po.random_complex(70, 11)
+    T, eigA = po.complex_schur(A)
+    n = T.shape[0]
+    x, y, _ = po.make_grid(po.vec2ax(eigA), 9, False)
+    q0 = po.start_vector(n, 3)
+    Z, algo, warned, it = po.psacore(T, q0, x, y, 1, want_iters=True)
+    Zc, itc, fl = co.grid(T, x, y, q0, nthreads=4)
+    floor = 1e-9 * np.linalg.norm(T)
+    worst = 0.0
+    for j in range(len(y)):
+        for k in range(len(x)):
+            s = po.sigmin_svd(T, x[k] + 1j * y[j])
+            if s > floor:
+                worst = max(worst, abs(Z[j, k] - s) / s, abs(Zc[j, k] - s) / s)
+    assert worst < 2e-4
+    ok = Z > floor
+    assert np.allclose(Zc[ok], Z[ok], rtol=1e-9)
+
+
+def test_shift_axes_property_based():
+    """hypothesis: for any window straddling the real axis the mirrored y axis is strictly increasing, symmetric where
+    it was mirrored and inside the window."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(lo=st.floats(-50.0, -0.01), hi=st.floats(0.01, 50.0), npts=st.integers(6, 300))
+    def check(lo, hi, npts):
+        ax = [-1.0, 1.0, lo, hi]
+        y, nm = po.shift_axes(ax, npts)
+        if len(y) < 2:
+            return
+        assert np.all(np.diff(y) > 0)
+        Z = np.abs(y)[:, None]
+        Zf, yf = po.unmirror(Z, y, nm)
+        assert np.all(np.diff(yf) > -1e-12 * (abs(hi) + abs(lo)))
+        assert np.allclose(Zf[:, 0], np.abs(yf))
+        assert yf[0] >= lo - 1e-9 * (hi - lo) and yf[-1] <= hi + 1e-9 * (hi - lo)
+
+    check()
