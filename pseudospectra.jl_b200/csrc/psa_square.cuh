@@ -191,20 +191,21 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 4) solve_kernel(SolveParams P) 
   //    instruction (UBLKCP), so per-lane bulk copies are serialised (~80 clk each); instead every thread issues
   //    16-byte cp.async copies (LDGSTS) for its share of the rows and hooks their completion onto the same
   //    mbarrier (one pre-counted arrival per thread).
+  const uint64_t pol_T = l2_policy_evict_last(), pol_X = l2_policy_evict_first();
   auto issue = [&](const StepCursor& pc, int stage) {
     unsigned char* sb = smem + stage * STAGE_BYTES;
     const bool needX = pc.c < CPB * pc.I;
     if (tid == 0) {
       mbar_arrive_expect_tx(&full_bar[stage], TILE_BYTES);
       const double2* src = (pc.phase ? P.packB : P.packA) + tile_index(pc.I, pc.c) * TILE_ELEMS;
-      bulk_g2s(sb, src, TILE_BYTES, &full_bar[stage]);
+      bulk_g2s_hint(sb, src, TILE_BYTES, &full_bar[stage], pol_T);
     }
     if (needX) {
       const int mem0 = pc.phase ? n_pad - KC * pc.c - KC : KC * pc.c;
 #pragma unroll
       for (int seg = tid; seg < NSV * KC; seg += SOLVE_THREADS) {  // 16-byte segments: row = seg / KC
         const int s = seg / KC, part = seg % KC;
-        cp_async16(sb + TILE_BYTES + s * XROW_BYTES + part * 16, wptr[s] + mem0 + part);
+        cp_async16_hint(sb + TILE_BYTES + s * XROW_BYTES + part * 16, wptr[s] + mem0 + part, pol_X);
       }
     }
     cp_async_mbar_arrive_noinc(&full_bar[stage]);  // arrives once this thread's copies (if any) have landed
