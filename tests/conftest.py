@@ -31,7 +31,13 @@ def pytest_collection_modifyitems(config, items):
 
 @pytest.fixture(scope="session")
 def pkg():
+    """The product package; builds libpsagpu.so first if the tree has not been built yet (nvcc cross-compiles
+    sm_100a without a GPU)."""
+    import subprocess
     import psa_b200_loader
+    lib = os.path.join(psa_b200_loader.PKG_DIR, "libpsagpu.so")
+    if not os.path.exists(lib):
+        subprocess.check_call(["make", "-s", "-C", ROOT, "all"])
     return psa_b200_loader.load_package()
 
 
