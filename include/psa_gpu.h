@@ -41,7 +41,8 @@ extern "C" {
 #define PSA_ALGO_SVD 4     /* :SVD     -- n < minlancs4psa (55): smallest singular value directly (compute.jl:478-519) */
 
 /* indices into the counts[] array returned by psa_gpu_grid */
-#define PSA_COUNT_NONCONVERGED 0 /* points where Lanczos hit maxit: shim raises the warning of compute.jl:603-606 */
+#define PSA_COUNT_NONCONVERGED 0 /* points where `lancz_converged` stayed false (maxit reached, or the bigsigma fallback,
+                                    which `break`s before the convergence test, compute.jl:654-656): warning of 603-606 */
 #define PSA_COUNT_EIGFAIL 1      /* points with the bigsigma fallback (non-finite recurrence): warning of compute.jl:607-610 */
 #define PSA_COUNT_TOTAL_ITERS 2  /* sum over points of Lanczos iterations (flop accounting: 8 n^2 per iteration) */
 #define PSA_COUNT_POINTS 3       /* points computed */
@@ -56,7 +57,12 @@ extern "C" {
 #define PSA_STAT_FLOPS 5         /* algorithmic real FP64 flops of the last call: 8 n^2 sum(iters) (+ QR for HessQR) */
 #define PSA_STAT_BYTES 6         /* algorithmic bytes for the HBM-bound HessQR path, 0 for sq_lanc */
 #define PSA_STAT_PACK_MS 7       /* device time of the one-time T packing in the last set_matrix */
-#define PSA_NSTATS 8
+#define PSA_STAT_MAX_DEVICE_MS 8 /* multi-device contexts: the slowest device's grid time (PSA_STAT_GRID_MS is device 0's) */
+#define PSA_NSTATS 9
+
+/* flags of psa_gpu_set_matrix_ex */
+#define PSA_MATRIX_DEFAULT 0
+#define PSA_MATRIX_UPPER_WRAPPER 1 /* T is the parent array of an `UpperTriangular` wrapper: ignore i > j without looking */
 
 /* Create a context driving `ngpus` devices from this process (devices 0..ngpus-1, or device_ids[0..ngpus-1]
  * when device_ids is non-null).  With ngpus > 1 the grid rows are sharded cyclically over the devices
@@ -77,6 +83,19 @@ int psa_gpu_init(int ngpus, const int* device_ids, void** ctx);
  * T: column-major, leading dimension ldt (>= m), interleaved complex128. */
 int psa_gpu_set_matrix(void* ctx, const double* T, int64_t ldt, int m, int n);
 
+/* Same with flags.  Without PSA_MATRIX_UPPER_WRAPPER a square T must satisfy `istriu(T)` -- the reference factorises
+ * anything else (`if !istriu(T1) F1 = factorize(T1)`, compute.jl:597-601), which is outside the GPU path: such input
+ * returns PSA_ERR_UNSUPPORTED so that the caller falls through to the host code.  Rectangular (n+1) x n input is
+ * always checked for upper-Hessenberg structure (lower bandwidth 2 is what `bw == 2` promises, compute.jl:579). */
+int psa_gpu_set_matrix_ex(void* ctx, const double* T, int64_t ldt, int m, int n, int flags);
+
+/* The reference's mutable `ComputeThresholds` (compute.jl:18-30): minlancs4psa (55; the SVD branch is used for
+ * n < minlancs4psa) and maxstdqr4hess (200; the Givens sweep is used for m > maxstdqr4hess, Householder-equivalent
+ * QR below).  Raising minlancs4psa is the reference's own way to get SVD "reference solutions" (compute.jl:18-21);
+ * the SVD kernel covers m*n <= 12288, larger shapes then return PSA_ERR_UNSUPPORTED at set_matrix.
+ * Takes effect at the next psa_gpu_set_matrix*.  maxit_lancs is the `maxit` argument of psa_gpu_grid. */
+int psa_gpu_set_thresholds(void* ctx, int minlancs4psa, int maxstdqr4hess);
+
 /* Device-resident variant: d_T is a device pointer on the context's first device (same layout). */
 int psa_gpu_set_matrix_device(void* ctx, const double* d_T, int64_t ldt, int m, int n);
 
@@ -85,7 +104,7 @@ int psa_gpu_set_matrix_device(void* ctx, const double* d_T, int64_t ldt, int m, 
  * q0 (unit norm, length >= n; the same vector for every point, compute.jl:207-210,622) and returns
  * Z[j + k*ly] = 1/sqrt(sigma) (compute.jl:611), column-major ly x lx.
  *   tol, maxit, bigsigma : psatol (1e-5), thresholds.maxit_lancs (99), 0.1*floatmax (compute.jl:88,27,475);
- *                          maxit above 126 is clamped to 126 (size of the per-shift alpha/beta history)
+ *                          1 <= maxit <= 4094 (PSA_ERR_ARG above: the per-shift alpha/beta history is sized from it)
  *   iters  : nullable, ly x lx int32, Lanczos iterations per point
  *   counts : nullable, PSA_NCOUNTS int64 (see PSA_COUNT_*)
  *   cancel : nullable; polled between scheduler ticks; *cancel == 1 -> PSA_ERR_CANCELLED (compute.jl:202-204)
@@ -93,6 +112,39 @@ int psa_gpu_set_matrix_device(void* ctx, const double* d_T, int64_t ldt, int m, 
 int psa_gpu_grid(void* ctx, const double* x, int lx, const double* y, int ly, const double* q0, double tol,
                  int maxit, double bigsigma, double* Z, int32_t* iters, int64_t* counts, int* algo,
                  volatile int* cancel);
+
+/* Row-batched start vectors: the reference draws a NEW random unit q for every batch of rows
+ * (`for j=ly:-step:1 ... q = randn(n) + randn(n)*im`, compute.jl:199-208).  q0s holds nbatch vectors of n
+ * interleaved complex (vector b at offset b*n); row_batch[j] in [0, nbatch) names the vector used by grid row j
+ * (for the reference's loop: row_batch[j] = (ly-1-j) / step with 0-based j).  With the shim drawing the vectors in
+ * the reference's order the whole psa_compute is reproducible draw for draw.  psa_gpu_grid == nbatch 1.
+ * Z may be NULL: the result then stays on the device for psa_gpu_postprocess. */
+int psa_gpu_grid_batched(void* ctx, const double* x, int lx, const double* y, int ly, const double* q0s, int nbatch,
+                         const int32_t* row_batch, double tol, int maxit, double bigsigma, double* Z, int32_t* iters,
+                         int64_t* counts, int* algo, volatile int* cancel);
+
+/* Device-side post-processing of the result of the last psa_gpu_grid* call, which is still resident on the
+ * context's first device: un-mirror for real matrices (compute.jl:222-235), `clamp!(Z, ps_tiny, Inf)` (236-238) and
+ * the reductions `recalc_levels` starts from (utils.jl:24-31).
+ *   y        : the ly computed grid rows (as passed to psa_gpu_grid); n_mirror as returned by shift_axes (0: none)
+ *   Zfull    : out, lyf x lx column-major (ldz >= lyf), lyf = ly + |n_mirror|;  yfull: out, lyf values
+ *   zstats   : out, [0] minimum(Z), [1] maximum(Z), [2] minimum over Z >= small_sigma (utils.jl:30; +Inf if none)
+ * Only one D2H copy of the final array is made. */
+int psa_gpu_postprocess(void* ctx, const double* y, int ly, int lx, int n_mirror, double ps_tiny, double small_sigma,
+                        double* Zfull, int64_t ldz, double* yfull, double* zstats);
+
+/* Pseudomode at one point (psmode_inv_lanczos, src/modes.jl:185-274, dense branch n >= 200): the same
+ * inverse-Lanczos recurrence on the resident square T, but the Lanczos basis is kept -- on the device -- and the
+ * right singular vector for sigma_min(zI - A) is assembled from the Ritz vector of the largest eigenvalue
+ * (`Q[:,1:end-1] * E.vectors[:,end]`, modes.jl:255-258).
+ *   q0 : start vector, n interleaved complex;  tol, num_its as in the reference
+ *   sigmin : out, Z = 1/sqrt(sigma);  mode : out, n interleaved complex;  iters : out (nullable)
+ *   info : out, 0 = converged; 1 = num_its reached -- the reference then returns NaN or falls back to a dense SVD
+ *          (modes.jl:262-272); sigmin/mode still hold the last iterate so the caller can choose.
+ * Needs the :sq_lanc path (m == n >= minlancs4psa); n < 200 is the reference's plain-SVD branch and stays on the
+ * host (PSA_ERR_UNSUPPORTED). */
+int psa_gpu_pseudomode(void* ctx, double zre, double zim, const double* q0, double tol, int num_its, double* sigmin,
+                       double* mode, int* iters, int* info);
 
 /* Same computation with every array already resident in device memory of the context's first device
  * (single-device contexts only): d_x[lx], d_y[ly], d_q0[2n], d_Z[ly*lx], d_iters[ly*lx] (nullable).

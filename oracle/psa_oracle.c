@@ -42,12 +42,17 @@ static int sturm_count(int l, const double* d, const double* e2, double x) {
 }
 
 static int tridiag_max_eig(int l, const double* d_in, const double* e_in, double* out) {
-  double d[128], e2[128];
-  if (l > 127) return -1;
+  double dbuf[128], ebuf[128];
+  double *d = dbuf, *e2 = ebuf;
+  if (l > 127) { /* maxit_lancs is mutable in the reference (compute.jl:27): no fixed limit here either */
+    d = (double*)malloc(sizeof(double) * 2 * (size_t)l);
+    if (!d) return -1;
+    e2 = d + l;
+  }
   double sc = 0;
   for (int i = 0; i < l; ++i) sc = fmax(sc, fabs(d_in[i]));
   for (int i = 0; i + 1 < l; ++i) sc = fmax(sc, fabs(e_in[i]));
-  if (sc == 0.0) { *out = 0.0; return 0; }
+  if (sc == 0.0) { *out = 0.0; if (d != dbuf) free(d); return 0; }
   double lo = 1e300, hi = -1e300;
   for (int i = 0; i < l; ++i) {
     d[i] = d_in[i] / sc;
@@ -63,6 +68,7 @@ static int tridiag_max_eig(int l, const double* d_in, const double* e_in, double
     if (sturm_count(l, d, e2, mid) >= l) hi = mid; else lo = mid;
   }
   *out = 0.5 * (lo + hi) * sc;
+  if (d != dbuf) free(d);
   return 0;
 }
 
@@ -102,11 +108,15 @@ double psa_oracle_lanczos(int n, const zc* U, int64_t ldt, double zre, double zi
                           int maxit, double bigsigma, zc* work, int32_t* iters_out, int32_t* flags_out) {
   zc z = zre + zim * I;
   zc *q = work, *qold = work + n, *v = work + 2 * (int64_t)n;
-  double alpha[128], beta_[128];
+  double abuf[128], bbuf[128];
+  double *alpha = abuf, *beta_ = bbuf;
+  if (maxit > 126) {
+    alpha = (double*)malloc(sizeof(double) * 2 * ((size_t)maxit + 2));
+    beta_ = alpha + maxit + 2;
+  }
   for (int i = 0; i < n; ++i) { q[i] = q0[i]; qold[i] = 0; }
   double beta = 0.0, sigold = 0.0, sigma = bigsigma;
   int converged = 0, failed = 0, l;
-  if (maxit > 126) maxit = 126;
   for (l = 1; l <= maxit; ++l) {
     solve_UH(n, U, ldt, z, q, v);
     solve_U(n, U, ldt, z, v);
@@ -123,6 +133,7 @@ double psa_oracle_lanczos(int n, const zc* U, int64_t ldt, double zre, double zi
     sigold = sigma;
   }
   if (l > maxit) l = maxit;
+  if (alpha != abuf) free(alpha);
   if (iters_out) *iters_out = l;
   if (flags_out) *flags_out = (converged ? 0 : 1) | (failed ? 2 : 0);
   return sigma;

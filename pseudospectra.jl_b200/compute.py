@@ -12,7 +12,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from ._lib import PsaGpu, PsaGpuCancelled
+from ._lib import PSA_ERR_UNSUPPORTED, PsaGpu, PsaGpuCancelled, PsaGpuUnsupported
 
 _FLOATMAX = float(np.finfo(np.float64).max)
 _FLOATMIN = float(np.finfo(np.float64).tiny)
@@ -38,14 +38,27 @@ def _context(ngpus: int) -> PsaGpu:
     return ctx
 
 
+def _matrix_key(T: np.ndarray, thresholds, upper_wrapper):
+    """Cheap identity of a matrix for the zoom cache: same buffer, shape and a sampled checksum (diagonal, first row,
+    last column).  A zoom re-enters psa_compute with the *same* Schur factor (src/zooming.jl:24-99 -> driver!), so
+    the upload and the packing are skipped when this key is unchanged."""
+    m, n = T.shape
+    k = min(m, n)
+    probe = complex(np.sum(T[np.arange(k), np.arange(k)])) + complex(np.sum(T[0, :])) + complex(np.sum(T[:, n - 1]))
+    return (T.__array_interface__["data"][0], T.shape, T.strides, str(T.dtype), probe,
+            thresholds.minlancs4psa, thresholds.maxstdqr4hess, bool(upper_wrapper))
+
+
 def psacore(T, S, q0, x, y, bw, *, tol=1e-5, threaded=False, nt=None, warned=None, thresholds=_default_thresholds,
-            ngpus=1, ctx: PsaGpu | None = None, want_iters=False, cancel=None, resident=False):
+            ngpus=1, ctx: PsaGpu | None = None, want_iters=False, cancel=None, resident=False, row_batch=None,
+            upper_wrapper=False, keep_on_device=False):
     """psacore(T,S,q,x,y,bw;tol) -> (Z, algo, warned)      [src/compute.jl:448-617]
 
     T: m x n (upper-triangular square, or (n+1) x n Hessenberg with bw == 2); S must be None / identity
-    (generalised problems are not on the GPU path); q0: unit start vector (length >= n); x, y: grid lines.
-    `threaded`/`nt` are accepted for signature parity and ignored.  `warned` carries the two once-only
-    warning flags of compute.jl:603-610.  With resident=True the matrix of `ctx` is reused (zoom recompute)."""
+    (generalised problems are not on the GPU path); q0: unit start vector (length >= n) -- or, with `row_batch`,
+    one vector per row batch; x, y: grid lines.  `threaded`/`nt` are accepted for signature parity and ignored.
+    `warned` carries the two once-only warning flags of compute.jl:603-610.  The matrix stays resident in `ctx`:
+    a second call with the same array (a zoom) skips the upload; resident=True forces the reuse."""
     if S is not None and not (np.isscalar(S) and S == 1):
         raise NotImplementedError("generalised problems (S != I) stay on the host path")
     warned = list(warned) if warned is not None else [False, False]
@@ -53,13 +66,21 @@ def psacore(T, S, q0, x, y, bw, *, tol=1e-5, threaded=False, nt=None, warned=Non
     m, n = T.shape
     if m < n:
         raise ValueError("Matrix size must be m x n with m >= n")  # compute.jl:459-461
-    own = ctx is None
-    if own:
+    if m != n and n >= thresholds.minlancs4psa and bw != 2:
+        # bw == 2 is the caller's promise of Hessenberg structure (compute.jl:579); anything wider is `qr(T1)` on a
+        # dense rectangular matrix, which stays on the host
+        raise PsaGpuUnsupported(PSA_ERR_UNSUPPORTED, "psacore", "rectangular input with bw != 2")
+    if ctx is None:
         ctx = _context(ngpus)
-    if not (resident and ctx.shape == (m, n)):
-        ctx.set_matrix(T)
+    key = _matrix_key(T, thresholds, upper_wrapper)
+    if not ((resident and ctx.shape == (m, n)) or getattr(ctx, "_matrix_key", None) == key):
+        ctx._matrix_key = None
+        ctx.set_thresholds(thresholds.minlancs4psa, thresholds.maxstdqr4hess)
+        ctx.set_matrix(T, upper_wrapper=upper_wrapper)
+        ctx._matrix_key = key
     Z, iters, counts, algo = ctx.grid(x, y, q0, tol=tol, maxit=thresholds.maxit_lancs, bigsigma=0.1 * _FLOATMAX,
-                                      want_iters=want_iters, cancel=cancel)
+                                      want_iters=want_iters, cancel=cancel, row_batch=row_batch,
+                                      want_Z=not keep_on_device)
     if counts[0] > 0 and not warned[0]:
         import warnings
         warnings.warn("Lanczos convergence failure(s) while computing resolvent norms")  # compute.jl:604
@@ -71,6 +92,21 @@ def psacore(T, S, q0, x, y, bw, *, tol=1e-5, threaded=False, nt=None, warned=Non
     if want_iters:
         return Z, algo, warned, iters
     return Z, algo, warned
+
+
+def _get_step_size(n, ly):
+    """Rows per psacore batch for Float64 (src/compute.jl:270-279)."""
+    if n < 100:
+        return max(1, ly // 8)
+    return min(ly, max(1, (4 * ly) // n))
+
+
+def row_batches(m, ly):
+    """Batch index of every grid row in the reference's loop `for j=ly:-step:1` (compute.jl:199-206): rows
+    j, j-1, ..., max(j-step+1, 1) share one start vector.  Returns (row_batch[ly] (0-based rows), nbatch)."""
+    step = _get_step_size(m, ly)
+    rb = (ly - 1 - np.arange(ly)) // step
+    return rb.astype(np.int32), int(rb.max()) + 1 if ly else 0
 
 
 # ---- grid / post-processing host logic (cheap; stays on the host exactly as in the reference) ----------
@@ -128,13 +164,17 @@ def _unmirror(Z, y, n_mirror):
     return np.vstack([Z[1:n_mirror + 1][::-1], Z]), np.concatenate([-y[1:n_mirror + 1][::-1], y])
 
 
-def recalc_levels(sigmin, ax):
-    """src/utils.jl:21-73"""
-    smin, smax = float(np.min(sigmin)), float(np.max(sigmin))
+def recalc_levels(sigmin, ax, zstats=None):
+    """src/utils.jl:21-73.  `zstats` = (min, max, min over values >= smallσ) when the device already reduced them
+    (psa_gpu_postprocess); otherwise they are taken from `sigmin` like the reference does (utils.jl:24-31)."""
+    if zstats is not None:
+        smin, smax = float(zstats[0]), float(zstats[1])
+    else:
+        smin, smax = float(np.min(sigmin)), float(np.max(sigmin))
     if smax <= _SMALL_SIGMA:
         return np.zeros(0), -2
     if smin <= _SMALL_SIGMA:
-        smin = float(np.min(sigmin[sigmin >= _SMALL_SIGMA]))
+        smin = float(zstats[2]) if zstats is not None else float(np.min(sigmin[sigmin >= _SMALL_SIGMA]))
     max_val, min_val = math.log10(smax), math.log10(smin)
     num_lines = 8
     last_lev = math.log10(0.03 * min(ax[3] - ax[2], ax[1] - ax[0]))
@@ -242,63 +282,36 @@ def psmode_inv_lanczos(A, q0, z, tol, num_its, *, fallbacksvd=False, ctx: PsaGpu
 
     Pseudomode at one point z: the same inverse-Lanczos recurrence as `_psa_lanczos!`, but the Lanczos basis is kept
     and the right singular vector for sigma_min(zI - A) is assembled from the Ritz vector (modes.jl:255-260).
-    The operator application v = T1^-1 (T2^-1 q), T2 = T1' (modes.jl:229) runs on the GPU through the solve kernel
-    (`psa_gpu_apply_resolvent`, one shift); A must be upper triangular (the Schur factor, as `modeplot` passes it).
-    n < 200 uses a plain host SVD exactly like the reference (modes.jl:193-200).  Returns (nan, nan) when the
-    iteration does not converge and fallbacksvd is False (modes.jl:262-272)."""
+    The whole recurrence, the basis and the final combination run on the GPU (`psa_gpu_pseudomode`); A must be upper
+    triangular (the Schur factor, as `modeplot` passes it).  n < 200 uses a plain host SVD exactly like the reference
+    (modes.jl:193-200).  Returns (nan, nan) when the iteration does not converge and fallbacksvd is False
+    (modes.jl:262-272)."""
     A = np.asarray(A)
     m, n = A.shape
     if m != n:
         raise ValueError("Matrix must be square")  # modes.jl:188
     z = complex(z)
-    q = np.asarray(q0, dtype=np.complex128).copy()
-    if n < 200:
+
+    def dense_svd():
         A1 = np.array(A, dtype=np.complex128)
         A1[np.arange(n), np.arange(n)] -= z
         U, S, Vh = np.linalg.svd(A1)
         return float(S[-1]), Vh[-1].conj()
+
+    if n < 200:
+        return dense_svd()
     if ctx is None:
         ctx = _context(1)
-    if not (resident and ctx.shape == (n, n)):
+    key = _matrix_key(A, _default_thresholds, False)
+    if not ((resident and ctx.shape == (n, n)) or getattr(ctx, "_matrix_key", None) == key):
+        ctx._matrix_key = None
+        ctx.set_thresholds(_default_thresholds.minlancs4psa, _default_thresholds.maxstdqr4hess)
         ctx.set_matrix(A)
-    H = np.zeros((num_its + 1, num_its + 1))
-    qold = np.zeros(n, dtype=np.complex128)
-    Q = [q.copy()]
-    beta, sigold, sigma, l = 0.0, 0.0, None, 0
-    for _ in range(num_its):
-        l += 1
-        v = ctx.apply_resolvent(np.array([z]), q[None, :])[0] - beta * qold
-        alpha = float(np.real(np.vdot(q, v)))
-        v = v - alpha * q
-        beta = float(np.linalg.norm(v))
-        qold = q
-        with np.errstate(all="ignore"):
-            q = v / beta
-        Q.append(q.copy())
-        H[l, l - 1] = H[l - 1, l] = beta
-        H[l - 1, l - 1] = alpha
-        try:
-            sigma = float(np.max(np.linalg.eigvalsh(H[:l, :l])))
-        except np.linalg.LinAlgError:
-            sigma = 1e308
-        with np.errstate(all="ignore"):
-            resid = abs(sigold / sigma - 1)
-        if resid < tol or beta == 0:
-            break
-        sigold = sigma
-    Z = 1.0 / math.sqrt(sigma)
-    try:
-        _, vecs = np.linalg.eigh(H[:l, :l])
-        qv = np.column_stack(Q[:l]) @ vecs[:, -1]
-    except np.linalg.LinAlgError:
-        l = num_its
-        qv = None
-    if l >= num_its:
+        ctx._matrix_key = key
+    Z, qv, l, info = ctx.pseudomode(z, q0, tol, num_its)
+    if info != 0:  # `if l >= num_its` (modes.jl:262)
         if fallbacksvd:
-            A1 = np.triu(np.array(A, dtype=np.complex128))
-            A1[np.arange(n), np.arange(n)] -= z
-            U, S, Vh = np.linalg.svd(A1)
-            return float(S[-1]), Vh[-1].conj()
+            return dense_svd()
         return float("nan"), float("nan")
     return Z, qv
 
@@ -327,13 +340,17 @@ def vec2ax(dispvec):
 
 
 def psa_compute(Targ, npts, ax, eigA, opts=None, S=None, *, psatol=1e-5, thresholds=_default_thresholds,
-                ctrlflag=None, q0=None, rng=None, ngpus=1, ctx: PsaGpu | None = None):
+                ctrlflag=None, q0=None, rng=None, ngpus=1, ctx: PsaGpu | None = None, per_batch_q=True,
+                upper_wrapper=False):
     """psa_compute(T,npts,ax,eigA,opts,S=I) -> (Z,x,y,levels,info,Tproj,eigAproj,algo)   [src/compute.jl:87-268]
 
     Dense branch with the GPU option switched on.  `opts` keys honoured: levels, recompute_levels, real_matrix,
-    scale_equal (proj_lev must be inf: projection is a host pre-step outside this path).  `ctrlflag` is a
-    one-element int32 numpy array; setting it to 1 cancels and returns None like compute.jl:202-204.
-    `q0`/`rng` supply the start vector the reference draws with randn (compute.jl:207-208)."""
+    scale_equal, proj_lev.  `ctrlflag` is a one-element int32 numpy array; setting it to 1 cancels and returns None
+    like compute.jl:202-204.  Start vectors: the reference draws a new unit `q` of length n(Targ) for every batch of
+    rows (compute.jl:199-208).  `q0` may be one vector (used for every batch), an (nbatch, n) array, or None: then
+    they are drawn from `rng` in the reference's order, one per batch (per_batch_q=False: one for the whole grid).
+    Un-mirroring, the clamp to ps_tiny and the min/max that feed `recalc_levels` run on the device
+    (`psa_gpu_postprocess`); only the final array crosses PCIe."""
     opts = dict(opts or {})
     Targ = np.asarray(Targ)
     m, n = Targ.shape
@@ -346,29 +363,41 @@ def psa_compute(Targ, npts, ax, eigA, opts=None, S=None, *, psatol=1e-5, thresho
     ax = [float(a) for a in ax]
     real_matrix = opts.get("real_matrix", not np.iscomplexobj(Targ))
     x, y, n_mirror = _grid(ax, npts, real_matrix, opts.get("scale_equal", False))
-    if q0 is None:
-        rng = rng or np.random.default_rng()
-        q0 = rng.standard_normal(n) + 1j * rng.standard_normal(n)
-        q0 = q0 / np.linalg.norm(q0)
+    ly = len(y)
     eigAproj = np.array(eigA)
     Tproj = Targ
     if m == n:  # compute.jl:147-153: projection only for square dense input
         Tproj, eigAproj = _maybe_project(Targ, opts.get("proj_lev", math.inf), ax, np.asarray(eigA), thresholds,
                                          opts.get("verbosity", 1))
-        m = n = Tproj.shape[0]
-        q0 = np.asarray(q0)[:n]
-        q0 = q0 / np.linalg.norm(q0) if len(q0) else q0
+        m = Tproj.shape[0]
+    nproj = Tproj.shape[1]
+    rb, nbatch = row_batches(m, ly)
+    if q0 is None:
+        rng = rng or np.random.default_rng()
+        nq = nbatch if per_batch_q else 1
+        q0 = np.empty((nq, n), dtype=np.complex128)
+        for b in range(nq):  # `q = randn(n) + randn(n)*im; q = q / norm(q)` with n = size(Targ, 2) (compute.jl:207-208)
+            v = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+            q0[b] = v / np.linalg.norm(v)
+    q0 = np.asarray(q0)
+    batched = q0.ndim == 2 and q0.shape[0] > 1
+    if q0.ndim == 2 and not batched:
+        q0 = q0[0]
+    # `q = q0[1:n]` (compute.jl:622): after a projection the vector is truncated, NOT renormalised
+    q0 = q0[..., :nproj]
+    if ctx is None:
+        ctx = _context(ngpus)
     try:
-        Z, algo, _ = psacore(Tproj, S, q0, x, y, m - n + 1, tol=psatol, thresholds=thresholds, ngpus=ngpus, ctx=ctx,
-                             cancel=ctrlflag)
+        _, algo, _ = psacore(Tproj, S, q0, x, y, m - nproj + 1, tol=psatol, thresholds=thresholds, ngpus=ngpus, ctx=ctx,
+                             cancel=ctrlflag, row_batch=rb if batched else None, upper_wrapper=upper_wrapper,
+                             keep_on_device=True)
     except PsaGpuCancelled:
         return None
-    Z, y = _unmirror(Z, y, n_mirror)
     ps_tiny = 10 * math.sqrt(_FLOATMIN)  # compute.jl:236-238
-    Z = np.clip(Z, ps_tiny, np.inf)
+    Z, y, zstats = ctx.postprocess(y, len(x), n_mirror, ps_tiny, _SMALL_SIGMA)
     err = 0
     if re_calc:
-        levels, err = recalc_levels(Z, ax)
-    elif np.min(levels) > math.log10(np.max(Z)) or np.max(levels) < math.log10(np.min(Z)):
-        levels, err = recalc_levels(Z, ax)  # compute.jl:255-260
+        levels, err = recalc_levels(Z, ax, zstats)
+    elif np.min(levels) > math.log10(zstats[1]) or np.max(levels) < math.log10(zstats[0]):
+        levels, err = recalc_levels(Z, ax, zstats)  # compute.jl:255-260
     return Z, x, y, levels, err, Tproj, eigAproj, algo

@@ -53,22 +53,21 @@ __device__ __forceinline__ void givens_cs(double2 f, double2 g, double& c, doubl
 // full_sweep = 1: :rect_qr on Hessenberg input: the reference calls qr(T1) (compute.jl:589), which also
 //   eliminates H[n+1,n]; for an upper Hessenberg matrix that is one more rotation, and R is unique up to unit row
 //   phases, which leave (R^H R) and hence sigma unchanged.
-__global__ void hess_qr_kernel(const int* __restrict__ fresh, int m, int n, const double2* __restrict__ H,
-                               const double2* __restrict__ zs, double2* __restrict__ Rall,
-                               const double2* __restrict__ q0, int n_pad, double2* __restrict__ Q0, int full_sweep) {
+__global__ void hess_qr_kernel(const int* __restrict__ fresh, const int* __restrict__ n_fresh, int m, int n,
+                               const double2* __restrict__ H, const double2* __restrict__ zs,
+                               double2* __restrict__ Rall, int full_sweep) {
   __shared__ double g_c[2];
   __shared__ double2 g_s[2];
-  const int slot = fresh[blockIdx.x];
   const int c = threadIdx.x;
+  // grid-stride over the fresh slots: the launch is sized from an upper bound (the host may be a few ticks behind)
+  for (int f = blockIdx.x; f < *n_fresh; f += gridDim.x) {
+  __syncthreads();  // g_c / g_s of the previous slot are no longer read
+  const int slot = fresh[f];
   const double2 z = zs[slot];
   const size_t rstride = 2 * (size_t)n * n + (size_t)((n + 31) / 32 * 32);
   double2* R = Rall + (size_t)slot * rstride;   // Rc: R[i,k] at k*n + i
   double2* Rr = R + (size_t)n * n;               // Rr: R[j,k] at j*n + k
   double2* rinv = Rr + (size_t)n * n;            // 1 / R[k,k]
-  // q <- q0 for this slot
-  double2* q = Q0 + (size_t)slot * n_pad;
-  for (int i = c; i < n_pad; i += blockDim.x) q[i] = (i < n) ? q0[i] : make_double2(0.0, 0.0);
-
   const bool live = c < n;
   const double2* Hc = H + (size_t)(live ? c : 0) * m;
   double2 carry = make_double2(0.0, 0.0);
@@ -129,6 +128,7 @@ __global__ void hess_qr_kernel(const int* __restrict__ fresh, int m, int n, cons
     Rr[(size_t)(n - 1) * n + c] = carry;
     rinv[n - 1] = crecip(carry);
   }
+  }
 }
 
 // One CTA per active slot: w = R^{-H} q (forward, dot form) then v = R^{-1} w (backward, axpy form); v -> Wv.
@@ -141,7 +141,15 @@ struct HessSolveParams {
   const double2* Q1;
   double2* Wv;
   const int* sel;
+  const int* iter;     // 0 = fresh slot: q is still the start vector of its row batch (read in place)
+  const int* batch;
+  const double2* q0;   // [nbatch][n_pad]
 };
+
+__device__ __forceinline__ const double2* hess_q_ptr(const HessSolveParams& P, int slot) {
+  return P.iter[slot] == 0 ? P.q0 + (size_t)P.batch[slot] * P.n_pad
+                           : (P.sel[slot] ? P.Q1 : P.Q0) + (size_t)slot * P.n_pad;
+}
 
 __global__ void __launch_bounds__(HS_THREADS) hess_solve_kernel(HessSolveParams P) {
   extern __shared__ __align__(16) unsigned char hsm[];
@@ -152,7 +160,7 @@ __global__ void __launch_bounds__(HS_THREADS) hess_solve_kernel(HessSolveParams 
   const int slot = P.active[blockIdx.x];
   const int n = P.n, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const double2* R = P.R + (size_t)slot * (2 * (size_t)n * n + (size_t)((n + 31) / 32 * 32));
-  const double2* q = (P.sel[slot] ? P.Q1 : P.Q0) + (size_t)slot * P.n_pad;
+  const double2* q = hess_q_ptr(P, slot);
   const int nb = (n + HB - 1) / HB;
 
   // ---- forward: (R^H) w = q ----
@@ -257,7 +265,7 @@ __global__ void __launch_bounds__(HW_THREADS) hess_solve_warp_kernel(HessSolvePa
   const double2* Rc = P.R + (size_t)slot * rstride;
   const double2* Rr = Rc + (size_t)n * n;
   const double2* rinv = Rr + (size_t)n * n;
-  const double2* q = (P.sel[slot] ? P.Q1 : P.Q0) + (size_t)slot * P.n_pad;
+  const double2* q = hess_q_ptr(P, slot);
   double2* ring = reinterpret_cast<double2*>(hwsm) + (size_t)warp * HW_DEPTH * n32;
   const double2 zero = make_double2(0.0, 0.0);
 
@@ -360,14 +368,18 @@ struct HessTick {
   double2* R;
   const double2* q0;
   const int* fresh;
-  int n_fresh;
+  int n_fresh;              // upper bound on the number of fresh slots (exact count: *n_fresh_dev)
+  const int* n_fresh_dev;
   const int* active;
-  int n_active;
+  int n_active;             // upper bound (exact count: *n_active_dev)
   const int* n_active_dev;
   double2 *Q0, *Q1, *Wv;
   const int* sel;
+  const int* iter;
+  const int* batch;
   const double2* z;
   int full_sweep;
+  int num_sms;
 };
 
 inline size_t hess_solve_smem(int n_pad) { return ((size_t)n_pad + HB * (HB + 1) + HB) * sizeof(double2); }
@@ -379,13 +391,13 @@ inline int hess_set_attrs() {
   return e == cudaSuccess ? 0 : -1;
 }
 
-// launches the tick's HessQR kernels; ev_a was recorded by the caller, ev_b is recorded here. Returns #launches.
-inline int hess_launch_tick(const HessTick& t, cudaStream_t stream, cudaEvent_t ev_a, cudaEvent_t ev_b) {
-  (void)ev_a;
+// launches the tick's HessQR kernels; the caller recorded the start event, ev_b is recorded here. Returns #launches.
+inline int hess_launch_tick(const HessTick& t, cudaStream_t stream, cudaEvent_t ev_b) {
   int launches = 0;
   if (t.n_fresh > 0) {
     const int threads = (t.n + 31) / 32 * 32;
-    hess_qr_kernel<<<t.n_fresh, threads, 0, stream>>>(t.fresh, t.m, t.n, t.H, t.z, t.R, t.q0, t.n_pad, t.Q0, t.full_sweep);
+    const int grid = t.n_fresh < 16 * t.num_sms ? t.n_fresh : 16 * t.num_sms;
+    hess_qr_kernel<<<grid, threads, 0, stream>>>(t.fresh, t.n_fresh_dev, t.m, t.n, t.H, t.z, t.R, t.full_sweep);
     ++launches;
   }
   HessSolveParams sp;
@@ -398,6 +410,9 @@ inline int hess_launch_tick(const HessTick& t, cudaStream_t stream, cudaEvent_t 
   sp.Q1 = t.Q1;
   sp.Wv = t.Wv;
   sp.sel = t.sel;
+  sp.iter = t.iter;
+  sp.batch = t.batch;
+  sp.q0 = t.q0;
   if (t.n <= 32 * HW_NPL)
     hess_solve_warp_kernel<<<(t.n_active + HW_THREADS / 32 - 1) / (HW_THREADS / 32), HW_THREADS, hess_warp_smem(t.n), stream>>>(sp);
   else

@@ -26,7 +26,8 @@ constexpr int SOLVE_THREADS = 128;            // 4 warps: one per SM sub-partiti
 __host__ __device__ constexpr int stage_bytes(int nsv) { return TILE_BYTES + nsv * XROW_BYTES; }
 __host__ __device__ constexpr int solve_smem(int nsv) { return STAGES * stage_bytes(nsv) + 64 + nsv * 16 + nsv * 8 * 2; }
 static_assert(STAGES * 8 <= 64, "mbarrier block");
-constexpr int HIST = 128;                     // per-slot alpha/beta history stride (maxit <= 126)
+constexpr int HIST_MIN = 128;                 // smallest per-slot alpha/beta history stride (maxit <= stride - 2)
+constexpr int HIST_MAX = 4096;                // largest supported stride (maxit <= 4094)
 
 __host__ __device__ inline long long tiles_per_phase(int nblk) { return 2LL * nblk * (nblk + 1); }
 // tile (I, c), c in [0, 4I+4): offset in tiles within one phase stream
@@ -128,6 +129,9 @@ struct SolveParams {
   double2* Wv;
   const int* sel;      // which of Q0/Q1 currently holds q
   const double2* z;    // per-slot shift
+  const int* iter;     // per-slot completed Lanczos iterations: 0 = fresh slot, q is still the start vector
+  const int* batch;    // per-slot start-vector index (row batch, compute.jl:199-208)
+  const double2* q0;   // [nbatch][n_pad] start vectors, zero padded
 };
 
 struct StepCursor {
@@ -169,7 +173,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 4) solve_kernel(SolveParams P) 
   if (tid < NSV) {
     const int slot = P.active[panel * NSV + tid];
     wptr[tid] = P.Wv + (size_t)slot * P.n_pad;
-    qptr[tid] = (P.sel[slot] ? P.Q1 : P.Q0) + (size_t)slot * P.n_pad;
+    // a fresh slot's q IS the start vector of its row batch: read it in place (lanczos_kernel materialises it)
+    qptr[tid] = P.iter[slot] == 0 ? P.q0 + (size_t)P.batch[slot] * P.n_pad
+                                  : (P.sel[slot] ? P.Q1 : P.Q0) + (size_t)slot * P.n_pad;
     zsh[tid] = P.z[slot];
   }
   if (tid == 0) {
@@ -391,45 +397,61 @@ struct SchedParams {
   const double* x;    // lx
   const double* y;    // ly (global)
   const int* order;   // nullable: queue position -> local point index (longest-job-first order)
+  const int* row_batch;  // nullable: global row -> start-vector index (per-batch q, compute.jl:199-208)
   int* slot_point;    // local point index or -1
   double2* slot_z;
   int* slot_iter;
   double* slot_beta;
   double* slot_sigold;
   int* slot_sel;
+  int* slot_batch;
   int* active;        // out, padded with W (the scratch slot) to a multiple of APAD
-  int* fresh;         // out, list of newly filled slots
+  int* fresh;         // out, list of newly filled slots (the HessQR path factorises those)
   int* state;         // [0]=next_point [1]=n_active [2]=n_fresh  (device)
-  int* host_state;    // mapped pinned mirror
+  unsigned long long* host_state;  // mapped pinned mirror: [0] = (tick << 32) | n_active, [1] = (tick << 32) | n_fresh
+  unsigned tick;      // sequence number of this tick (1, 2, ...)
 };
 
+// exclusive scan of one int per thread over a 1024-thread block (warp shuffles + one shared-memory hop);
+// returns the exclusive prefix, leaves the block total in *total_s
+__device__ __forceinline__ int block_exscan_1024(int v, int* wsum /* 32 ints */, int* total_s) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();  // protects wsum / total_s from the previous use
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = wsum[lane], winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    wsum[lane] = winc - w;
+    if (lane == 31) *total_s = winc;
+  }
+  __syncthreads();
+  return wsum[warp] + inc - v;
+}
+
 __global__ void __launch_bounds__(1024) sched_kernel(SchedParams S) {
-  __shared__ int scan[1024];
-  __shared__ int base_s;
+  __shared__ int wsum[32];
+  __shared__ int total_s;
   const int tid = threadIdx.x;
   const int C = (S.W + 1023) / 1024;
-  const int lo = tid * C, hi = min(S.W, lo + C);
+  const int lo = min(S.W, tid * C), hi = min(S.W, lo + C);
   const int head = S.state[0];
-  auto exscan = [&](int v) -> int {  // exclusive scan over the block; total left in base_s
-    scan[tid] = v;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      int t = (tid >= o) ? scan[tid - o] : 0;
-      __syncthreads();
-      scan[tid] += t;
-      __syncthreads();
-    }
-    if (tid == 1023) base_s = scan[1023];
-    const int ex = scan[tid] - v;
-    __syncthreads();
-    return ex;
-  };
   int idle = 0;
   for (int i = lo; i < hi; ++i) idle += (S.slot_point[i] < 0);
-  int rank = exscan(idle);
-  const int total_idle = base_s;
-  __syncthreads();
+  int rank = block_exscan_1024(idle, wsum, &total_s);
+  const int total_idle = total_s;
   const int n_fresh = max(0, min(total_idle, S.P - head));
+  int act = 0;
   for (int i = lo; i < hi; ++i) {
     if (S.slot_point[i] < 0) {
       const int qpos = head + rank;
@@ -443,15 +465,17 @@ __global__ void __launch_bounds__(1024) sched_kernel(SchedParams S) {
         S.slot_beta[i] = 0.0;
         S.slot_sigold[i] = 0.0;
         S.slot_sel[i] = 0;
+        S.slot_batch[i] = S.row_batch ? S.row_batch[j] : 0;
         S.fresh[rank] = i;
+        ++act;
       }
       ++rank;
+    } else {
+      ++act;
     }
   }
-  int act = 0;
-  for (int i = lo; i < hi; ++i) act += (S.slot_point[i] >= 0);
-  int arank = exscan(act);
-  const int n_active = base_s;
+  int arank = block_exscan_1024(act, wsum, &total_s);
+  const int n_active = total_s;
   for (int i = lo; i < hi; ++i)
     if (S.slot_point[i] >= 0) S.active[arank++] = i;
   const int padded = (n_active + APAD - 1) / APAD * APAD;
@@ -460,19 +484,13 @@ __global__ void __launch_bounds__(1024) sched_kernel(SchedParams S) {
     S.state[0] = head + n_fresh;
     S.state[1] = n_active;
     S.state[2] = n_fresh;
-    S.host_state[0] = head + n_fresh;
-    S.host_state[1] = n_active;
-    S.host_state[2] = n_fresh;
+    if (n_active > 0) S.state[3] += 1;  // live ticks so far
+    volatile unsigned long long* hs = S.host_state;
+    hs[1] = ((unsigned long long)S.tick << 32) | (unsigned)n_fresh;
+    __threadfence_system();
+    hs[0] = ((unsigned long long)S.tick << 32) | (unsigned)n_active;  // the word the host polls, written last
     __threadfence_system();
   }
-}
-
-// q <- q0 for freshly filled slots (qold needs no init: its first use is multiplied out, see lanczos_kernel)
-__global__ void init_fresh_kernel(const int* __restrict__ fresh, int n_pad, int n, const double2* __restrict__ q0,
-                                  double2* __restrict__ Q0) {
-  const int slot = fresh[blockIdx.x];
-  double2* q = Q0 + (size_t)slot * n_pad;
-  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) q[i] = (i < n) ? q0[i] : make_double2(0.0, 0.0);
 }
 
 // ---- largest eigenvalue of the l x l Lanczos tridiagonal, one warp, 32-way multisection Sturm counts ---
@@ -536,8 +554,11 @@ struct LanczosParams {
   double* slot_beta;
   double* slot_sigold;
   int* slot_sel;
-  double* hist_alpha;  // [W][HIST]
+  const int* slot_batch;
+  const double2* q0;   // [nbatch][n_pad] start vectors
+  double* hist_alpha;  // [W+1][hist]
   double* hist_beta;
+  int hist;            // history stride (>= maxit + 2); also sizes the dynamic shared memory (2 * hist doubles)
   double tol;
   int maxit;
   double bigsigma;
@@ -550,7 +571,9 @@ constexpr int LZ_THREADS = 256;
 
 __global__ void __launch_bounds__(LZ_THREADS) lanczos_kernel(LanczosParams L) {
   __shared__ double red[LZ_THREADS / 32];
-  __shared__ double sd[HIST], se2[HIST];
+  extern __shared__ double lz_dyn[];
+  double* sd = lz_dyn;
+  double* se2 = lz_dyn + L.hist;
   if ((int)blockIdx.x >= *L.n_active) return;
   const int slot = L.active[blockIdx.x];
   const int tid = threadIdx.x;
@@ -561,18 +584,23 @@ __global__ void __launch_bounds__(LZ_THREADS) lanczos_kernel(LanczosParams L) {
   double2* w = L.Wv + (size_t)slot * L.n_pad;
   const int l = L.slot_iter[slot] + 1;
   const double beta_old = L.slot_beta[slot];
+  // first iteration of a point: q is the start vector of its row batch (`q = q0[1:n]`, compute.jl:622); it is
+  // materialised into the slot here (the solve kernel read it in place), so no separate init pass is needed
+  const double2* qsrc = (l == 1) ? L.q0 + (size_t)L.slot_batch[slot] * L.n_pad : q;
 
   // v = w - beta*qold ; alpha = Re(q . v)
   double part = 0.0;
   for (int i = tid; i < n; i += LZ_THREADS) {
     double2 v = w[i];
+    const double2 qq = qsrc[i];
     if (l > 1) {
       const double2 o = qold[i];
       v.x -= beta_old * o.x;
       v.y -= beta_old * o.y;
       w[i] = v;
+    } else {
+      q[i] = qq;
     }
-    const double2 qq = q[i];
     part = fma(qq.x, v.x, part);
     part = fma(qq.y, v.y, part);
   }
@@ -618,8 +646,8 @@ __global__ void __launch_bounds__(LZ_THREADS) lanczos_kernel(LanczosParams L) {
     qold[i] = make_double2(v.x / beta, v.y / beta);
   }
 
-  double* ha = L.hist_alpha + (size_t)slot * HIST;
-  double* hb = L.hist_beta + (size_t)slot * HIST;
+  double* ha = L.hist_alpha + (size_t)slot * L.hist;
+  double* hb = L.hist_beta + (size_t)slot * L.hist;
   const bool finite_ab = isfinite(alpha) && isfinite(beta);
   if (tid == 0) {
     ha[l - 1] = alpha;
@@ -665,7 +693,7 @@ __global__ void __launch_bounds__(LZ_THREADS) lanczos_kernel(LanczosParams L) {
         L.Z[p] = 1.0 / sqrt(sigma);
         if (L.iters) L.iters[p] = l;
         L.slot_point[slot] = -1;
-        if (!conv && !failed) atomicAdd(&L.counts[0], 1ull);
+        if (!conv) atomicAdd(&L.counts[0], 1ull);  // incl. fallback points (compute.jl:654-656 leaves lancz_converged false)
         if (failed) atomicAdd(&L.counts[1], 1ull);
         atomicAdd(&L.counts[2], (unsigned long long)l);
         atomicAdd(&L.counts[3], 1ull);
@@ -682,7 +710,7 @@ __global__ void __launch_bounds__(LZ_THREADS) lanczos_kernel(LanczosParams L) {
 // ---- helpers for the apply_resolvent diagnostic hook ---------------------------------------------------
 __global__ void load_slots_kernel(int ns, int n, int n_pad, const double2* __restrict__ Q, const double2* __restrict__ z,
                                   double2* __restrict__ Q0, double2* __restrict__ slot_z, int* __restrict__ slot_sel,
-                                  int* __restrict__ active, int W, int* __restrict__ state) {
+                                  int* __restrict__ slot_iter, int* __restrict__ active, int W, int* __restrict__ state) {
   const int s = blockIdx.x;
   if (s < ns) {
     double2* q = Q0 + (size_t)s * n_pad;
@@ -690,6 +718,7 @@ __global__ void load_slots_kernel(int ns, int n, int n_pad, const double2* __res
     if (threadIdx.x == 0) {
       slot_z[s] = z[s];
       slot_sel[s] = 0;
+      slot_iter[s] = 1;  // not a fresh slot: the solve kernel reads q from Q0
       active[s] = s;
     }
   } else if (threadIdx.x == 0) {
@@ -701,6 +730,55 @@ __global__ void load_slots_kernel(int ns, int n, int n_pad, const double2* __res
 __global__ void store_slots_kernel(int n, int n_pad, const double2* __restrict__ Wv, double2* __restrict__ V) {
   const int s = blockIdx.x;
   for (int i = threadIdx.x; i < n; i += blockDim.x) V[(size_t)s * n + i] = Wv[(size_t)s * n_pad + i];
+}
+
+// ---- host-side launch helpers --------------------------------------------------------------------------------
+// Panel width for a tick.  The solve kernel runs 4-warp CTAs (one warp per SM sub-partition), up to 4 per SM, each
+// owning a panel of 32, 16 or 8 shifts.  Wide panels reuse each T tile for more shifts; narrow ones spread the
+// active shifts over every SM when few are active (grid tails, strong scaling over many GPUs).  The choice
+// minimises a small cost model measured on B200 (profiles/r01_panel_sweep.txt): launch time, relative to a full
+// launch, with k = 1..4 co-resident CTAs per SM; more panels than that run in rounds.
+inline int pick_panel_width(int n_active, int num_sms) {
+  const char* env = getenv("PSA_PANEL_WIDTH");  // experiments only
+  const int forced = env ? atoi(env) : 0;
+  if (forced == 32 || forced == 16 || forced == 8) return forced;
+  static const int widths[3] = {8, 16, 32};
+  static const double cost[3][5] = {{0.0, 0.131, 0.162, 0.223, 0.280},   // width 8:  k = 1..4 CTAs per SM
+                                    {0.0, 0.207, 0.290, 0.406, 0.519},   // width 16
+                                    {0.0, 0.349, 0.509, 0.772, 1.000}};  // width 32
+  int best = 32;
+  double best_cost = 1e300;
+  for (int i = 0; i < 3; ++i) {
+    const int panels = (n_active + widths[i] - 1) / widths[i];
+    const int per_sm = (panels + num_sms - 1) / num_sms;  // CTAs on the busiest SM
+    const double c = (per_sm / 4) * cost[i][4] + cost[i][per_sm % 4];
+    if (c < best_cost - 1e-12) {
+      best_cost = c;
+      best = widths[i];
+    }
+  }
+  return best;
+}
+
+inline int solve_set_attrs() {
+  cudaError_t e = cudaFuncSetAttribute(solve_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem(32));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem(16));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem(8));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  return e == cudaSuccess ? 0 : -1;
+}
+
+// n_active is an upper bound of the device-side count (panels past it exit at once)
+inline void launch_solve(const SolveParams& sp, int n_active, int num_sms, cudaStream_t stream) {
+  const int width = pick_panel_width(n_active, num_sms);
+  const int panels = (n_active + width - 1) / width;
+  switch (width) {
+    case 32: solve_kernel<32><<<panels, SOLVE_THREADS, solve_smem(32), stream>>>(sp); break;
+    case 16: solve_kernel<16><<<panels, SOLVE_THREADS, solve_smem(16), stream>>>(sp); break;
+    default: solve_kernel<8><<<panels, SOLVE_THREADS, solve_smem(8), stream>>>(sp); break;
+  }
 }
 
 }  // namespace psa

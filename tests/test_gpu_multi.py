@@ -48,3 +48,25 @@ def test_two_device_hessqr(pkg):
         g2.set_matrix(H)
         Z2, it2, _, algo = g2.grid(x, y, q0)
     assert algo == "HessQR" and np.array_equal(Z1, Z2) and np.array_equal(it1, it2)
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+def test_multi_device_batched_q_and_device_postprocess(pkg):
+    """Per-batch start vectors and the device-side assembly + post-processing on a multi-device context: the tiles are
+    interleaved on device 0 (no host loop), un-mirrored and clamped there; bitwise equal to the single-device result."""
+    T, eigA = po.complex_schur(po.grcar(96))
+    x, y, nm = po.make_grid([-1.0, 3.0, -3.0, 4.0], 21, True)
+    from pseudospectra_jl_b200 import compute as hc
+    rb, nb = hc.row_batches(96, len(y))
+    qs = np.stack([po.start_vector(96, 40 + b) for b in range(nb)])
+    res = []
+    for ng in (1, min(_ngpus(), 4)):
+        with pkg.PsaGpu(ng) as g:
+            g.set_matrix(T)
+            Z, it, c, _ = g.grid(x, y, qs, row_batch=rb)
+            Zf, yf, zs = g.postprocess(y, len(x), nm, po.PS_TINY)
+            res.append((Z, it, c, Zf, yf, zs))
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    Zo, yo = po.unmirror(res[0][0], y, nm)
+    assert np.array_equal(res[0][3], np.clip(Zo, po.PS_TINY, np.inf)) and np.array_equal(res[0][4], yo)

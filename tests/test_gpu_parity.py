@@ -53,7 +53,7 @@ def test_solve_kernel_is_linear_and_ignores_strict_lower_part(gpu):
     z = 4 * (rng.standard_normal(ns) + 1j * rng.standard_normal(ns))
     Q1 = rng.standard_normal((ns, n)) + 1j * rng.standard_normal((ns, n))
     Q2 = rng.standard_normal((ns, n)) + 1j * rng.standard_normal((ns, n))
-    gpu.set_matrix(A)
+    gpu.set_matrix(A, upper_wrapper=True)  # parent array of an UpperTriangular wrapper: i > j ignored, explicitly
     V1, V2, V12 = gpu.apply_resolvent(z, Q1), gpu.apply_resolvent(z, Q2), gpu.apply_resolvent(z, Q1 + 2j * Q2)
     assert np.allclose(V12, V1 + 2j * V2, rtol=1e-10, atol=1e-12 * np.abs(V12).max())
     gpu.set_matrix(np.triu(A))
@@ -256,8 +256,8 @@ def test_plain_c_driver_matches_oracle(pkg, tmp_path):
 
 
 def test_pseudomode_inverse_lanczos(pkg):
-    """psmode_inv_lanczos (modes.jl:185-274): sigma_min and the pseudomode at one point, with the
-    operator applications on the GPU; compared with the oracle's restatement and with the defining residual."""
+    """psmode_inv_lanczos (modes.jl:185-274): sigma_min and the pseudomode at one point through the
+    reference-shaped Python mirror; compared with the oracle's restatement and with the defining residual."""
     T, eigA = po.complex_schur(po.random_complex(320, 9))
     q0 = po.start_vector(320, 4)
     for z in (2.0 + 1.5j, -25.0 + 3.0j):
@@ -279,6 +279,15 @@ def test_unsupported_shapes_raise(pkg, gpu):
         gpu.set_matrix(A)  # rectangular but not Hessenberg: rect_fact makes it a generalised problem (host path)
     with pytest.raises(pkg.PsaGpuUnsupported):
         gpu.set_matrix(np.ones((300, 250)))  # bw > 2
+    with pytest.raises(pkg.PsaGpuUnsupported):
+        gpu.set_matrix(np.ones((301, 300)))  # m == n+1 > 200 but dense below the sub-diagonal: not :HessQR input
+    with pytest.raises(pkg.PsaGpuUnsupported):
+        # square but not upper triangular (new_matrix hands A itself over when schur fails): the reference
+        # factorises it (`if !istriu(T1) F1 = factorize(T1)`, compute.jl:597-601) -- host path, never silently wrong
+        gpu.set_matrix(np.triu(np.ones((80, 80))) + np.eye(80, k=-3))
+    with pytest.raises(pkg.PsaGpuUnsupported):
+        pkg.psacore(np.triu(np.ones((301, 300)), -1), None, np.ones(300), [0.0], [0.0], 3, ctx=gpu)  # bw != 2
+    assert gpu.shape is None  # a rejected matrix leaves no stale shape behind
     with pytest.raises(pkg.PsaGpuError):
         pkg.PsaGpu(1).grid([0.0], [0.0], np.ones(4))  # no matrix set
 
@@ -317,3 +326,188 @@ def test_conjugate_symmetry_large_real_matrix(gpu):
     assert ok.sum() >= 24 and np.allclose(Zp[ok], Zm[ok], rtol=1e-3)
     Zc, _, _ = co.grid(T, x, y, q0, nthreads=8)
     assert _rel(Zp, Zc, _floor(T)) < RTOL
+
+
+# ---- round 2: the rest of the boundary ---------------------------------------------------------------------------
+
+def test_thresholds_are_mutable_like_the_reference(gpu):
+    """compute.jl:18-30: raising minlancs4psa forces the SVD branch ("reference solutions"), lowering it sends a small
+    matrix through the Lanczos path; maxstdqr4hess moves the HessQR / rect_qr boundary."""
+    T, eigA = po.complex_schur(po.random_complex(60, 8))
+    x, y = np.linspace(-6, 6, 7), np.linspace(-5, 5, 6)
+    q0 = po.start_vector(60, 3)
+    try:
+        gpu.set_thresholds(100, 200)
+        gpu.set_matrix(T)
+        Zs, its, _, algo = gpu.grid(x, y, q0)
+        assert algo == "SVD" and its.max() == 0
+        svd = np.array([[po.sigmin_svd(T, xx + 1j * yy) for xx in x] for yy in y])
+        assert np.max(np.abs(Zs - svd) / svd) < 1e-10
+        gpu.set_thresholds(55, 200)
+        gpu.set_matrix(T)
+        Zl, itl, _, algo = gpu.grid(x, y, q0)
+        assert algo == "sq_lanc" and np.max(np.abs(Zl - svd) / svd) < 1e-4  # Lanczos at tol 1e-5 vs its own SVD solution
+        gpu.set_thresholds(20, 200)
+        T30 = np.asfortranarray(T[:30, :30])
+        gpu.set_matrix(T30)
+        Z30, it30, _, algo = gpu.grid(x, y, q0[:30] / np.linalg.norm(q0[:30]))
+        Zc, itc, _ = co.grid(T30, x, y, q0[:30] / np.linalg.norm(q0[:30]))
+        assert algo == "sq_lanc" and _rel(Z30, Zc) < RTOL and np.array_equal(it30, itc)
+        H = np.asfortranarray(po.grcar(190)[:, :-1]).astype(complex)  # 190 x 189
+        gpu.set_thresholds(55, 150)
+        gpu.set_matrix(H)
+        Zh, _, _, algo = gpu.grid(x[:3], y[:2], po.start_vector(189, 1))
+        Zhc, _, _ = co.grid(H, x[:3], y[:2], po.start_vector(189, 1))  # the C oracle's m != n branch is the Givens sweep
+        assert algo == "HessQR" and _rel(Zh, Zhc, _floor(H)) < RTOL
+    finally:
+        gpu.set_thresholds(55, 200)
+
+
+def test_per_batch_start_vectors_match_reference_loop(pkg, gpu):
+    """The reference draws a new q per row batch (compute.jl:199-208).  With the same per-batch vectors the GPU path
+    reproduces the oracle's row-batched psa_compute point for point."""
+    T, eigA = po.complex_schur(po.readme_matrix(150))
+    ax = po.vec2ax(eigA)
+    npts = 22
+    from pseudospectra_jl_b200 import compute as hc
+    rb, nb = hc.row_batches(150, npts)
+    assert po.get_step_size(150, npts) == 1 and nb == 22
+    qs = np.stack([po.start_vector(150, 100 + b) for b in range(nb)])
+    out = pkg.psa_compute(T, npts, ax, eigA, {}, q0=qs, ctx=gpu)
+    ref = po.psa_compute(T, npts, ax, eigA, {}, q_for_batch=lambda b, n: qs[b])
+    assert out[7] == ref[7] == "sq_lanc"
+    assert np.array_equal(out[1], ref[1]) and np.array_equal(out[2], ref[2])
+    assert _rel(out[0], ref[0]) < RTOL and np.allclose(out[3], ref[3])
+    # n < 100 rule: ly // 8 rows per batch
+    T60, e60 = po.complex_schur(po.random_complex(60, 2))
+    rb60, nb60 = hc.row_batches(60, 20)
+    assert nb60 == 10 and list(rb60[-2:]) == [0, 0] and rb60[0] == 9
+    qs60 = np.stack([po.start_vector(60, 7 + b) for b in range(nb60)])
+    out = pkg.psa_compute(T60, 20, [-8, 8, -8, 8], e60, {}, q0=qs60, ctx=gpu)
+    ref = po.psa_compute(T60, 20, [-8, 8, -8, 8], e60, {}, q_for_batch=lambda b, n: qs60[b])
+    assert _rel(out[0], ref[0]) < RTOL
+
+
+@pytest.mark.parametrize("ax,npts", [([-1.44, 3.24, -3.8, 3.8], 20), ([-1, 2, -3, 4], 21), ([-1, 2, -4, 3], 20),
+                                      ([-2, 2, -2, 2], 15), ([-2, 2, -2, 2], 16), ([-1, 2, 0.5, 4], 9)])
+def test_device_postprocess_matches_reference_rules(gpu, ax, npts):
+    """psa_gpu_postprocess = un-mirror (compute.jl:222-235) + clamp (236-238) + min/max for recalc_levels, for every
+    branch of shift_axes (top master, bottom master, symmetric with / without a row at y = 0, no symmetry)."""
+    T, eigA = po.complex_schur(po.grcar(64))
+    x, y, nm = po.make_grid(ax, npts, True)
+    q0 = po.start_vector(64, 0)
+    gpu.set_matrix(T)
+    Z, _, _, _ = gpu.grid(x, y, q0)
+    Z2, _, _, _ = gpu.grid(x, y, q0, want_Z=False)
+    assert Z2 is None
+    tiny = float(np.median(Z))  # a clamp level that actually bites
+    Zf, yf, zs = gpu.postprocess(y, len(x), nm, tiny, 1e-150)
+    Zo, yo = po.unmirror(Z, y, nm)
+    Zo = np.clip(Zo, tiny, np.inf)
+    assert np.array_equal(yf, yo) and np.array_equal(Zf, Zo)
+    assert zs[0] == Zo.min() and zs[1] == Zo.max() and zs[2] == Zo[Zo >= 1e-150].min()
+
+
+def test_pseudomode_through_the_c_abi(pkg, gpu):
+    """psa_gpu_pseudomode (modes.jl:185-274): basis kept on the device; against the oracle's restatement, the dense SVD
+    and the defining residual."""
+    T, eigA = po.complex_schur(po.random_complex(320, 9))
+    q0 = po.start_vector(320, 4)
+    gpu.set_matrix(T)
+    for z in (2.0 + 1.5j, -25.0 + 3.0j):
+        Zg, qg, l, info = gpu.pseudomode(z, q0, 1e-10, 60)
+        Zo, qo, lo = po.psmode_inv_lanczos(T, q0, z, 1e-10, 60)
+        assert info == 0 and l == lo and abs(Zg - Zo) <= 1e-8 * Zo
+        ph = np.vdot(qo, qg) / abs(np.vdot(qo, qg))
+        assert np.linalg.norm(qg - ph * qo) <= 1e-6 * np.linalg.norm(qo)
+        s = po.sigmin_svd(T, z)
+        assert abs(Zg - s) <= 1e-6 * s
+        assert abs(np.linalg.norm((T - z * np.eye(320)) @ qg) / np.linalg.norm(qg) - s) <= 1e-4 * s
+    Zn, qn, l, info = gpu.pseudomode(2.0 + 1.5j, q0, 1e-14, 3)  # cannot converge in 3 steps: info = 1 (modes.jl:262)
+    assert info == 1 and l == 3
+    assert np.isnan(pkg.psmode_inv_lanczos(T, q0, 2.0 + 1.5j, 1e-14, 3, ctx=gpu)[0])
+    with pytest.raises(pkg.PsaGpuUnsupported):
+        gpu.set_matrix(T[:150, :150])
+        gpu.pseudomode(1.0, q0[:150], 1e-8, 30)  # n < 200: the reference's plain-SVD branch stays on the host
+
+
+def test_maxit_above_126_and_fallback_counts(gpu):
+    """maxit_lancs is mutable (compute.jl:27): no silent clamp.  Fallback points count as non-converged too
+    (compute.jl:654-656 `break`s with lancz_converged false, so both warnings fire)."""
+    T, _ = po.complex_schur(po.random_complex(120, 5))
+    q0 = po.start_vector(120, 0)
+    gpu.set_matrix(T)
+    x, y = np.linspace(-9, 9, 6), np.linspace(-9, 9, 5)
+    Z, it, counts, _ = gpu.grid(x, y, q0, tol=1e-15, maxit=150)  # unreachable tolerance: every point runs 150 iterations
+    Zc, itc, flc = co.grid(T, x, y, q0, tol=1e-15, maxit=150)
+    assert it.max() > 126 and np.array_equal(it, itc) and _rel(Z, Zc) < RTOL and counts[0] == (flc & 1).sum()
+    Tg, _ = po.complex_schur(po.grcar(400))
+    gpu.set_matrix(Tg)
+    Z, it, counts, _ = gpu.grid(np.linspace(0.2, 2.0, 10), np.linspace(0.1, 2.5, 9), po.start_vector(400, 0))
+    Zc, itc, flc = co.grid(Tg, np.linspace(0.2, 2.0, 10), np.linspace(0.1, 2.5, 9), po.start_vector(400, 0))
+    assert counts[1] == ((flc & 2) != 0).sum() > 0 and counts[0] == ((flc & 1) != 0).sum() >= counts[1]
+
+
+def test_zoom_reuses_the_resident_matrix(pkg, gpu):
+    """A zoom re-enters psa_compute with the same Schur factor (zooming.jl:24-99): the upload + packing are skipped."""
+    T, eigA = po.complex_schur(po.random_complex(700, 12))
+    q0 = po.start_vector(700, 0)
+    gpu._matrix_key = None
+    calls = []
+    orig = gpu.set_matrix
+    gpu.set_matrix = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    try:
+        o1 = pkg.psa_compute(T, 10, [-30, 30, -30, 30], eigA, {}, q0=q0, ctx=gpu)
+        o2 = pkg.psa_compute(T, 10, [-5, 5, -5, 5], eigA, {}, q0=q0, ctx=gpu)  # zoom
+        assert len(calls) == 1
+        T2 = T.copy()
+        T2[0, 5] += 1.0
+        pkg.psa_compute(T2, 4, [-5, 5, -5, 5], eigA, {}, q0=q0, ctx=gpu)      # a different matrix is uploaded
+        assert len(calls) == 2
+    finally:
+        gpu.set_matrix = orig
+    x, y, _ = po.make_grid([-5, 5, -5, 5], 10, False)
+    Zc, _, _ = co.grid(T, x, y, q0, nthreads=8)
+    assert _rel(o2[0], np.clip(Zc, po.PS_TINY, np.inf)) < RTOL
+
+
+def test_plain_c_driver_full_boundary(pkg, tmp_path):
+    """thresholds / grid_batched / postprocess / pseudomode driven from plain C, checked against the oracle."""
+    import subprocess
+    from test_host import _build_abi_driver
+    n, lx, ly = 208, 5, 4
+    r = subprocess.run([_build_abi_driver(pkg, tmp_path), str(n), str(lx), str(ly), "full"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    T = np.where(i < j, 0.3 * np.sin(1.0 + i + 2.0 * j) + 0.3j * np.cos(2.0 + 3.0 * i + j), 0)
+    T = np.asfortranarray(T + np.diag(0.05 * np.arange(n) - 1.0 + 0.02j * np.arange(n)))
+    x = np.array([-2.0 + 4.0 * k / (lx - 1) for k in range(lx)])
+    y = np.array([-1.0 + 3.0 * jj / (ly - 1) for jj in range(ly)])
+    q0 = np.cos(0.7 * np.arange(n)) + 1j * np.sin(1.3 * np.arange(n) + 0.2)
+    q0 = q0 / np.linalg.norm(q0)
+    q1 = np.conj(q0[::-1])
+    Zb = np.zeros((ly, lx))
+    itb = np.zeros((ly, lx), dtype=int)
+    for jj in range(ly):
+        Zr, itr, _ = co.grid(T, x, y[jj:jj + 1], q1 if jj & 1 else q0, maxit=150)
+        Zb[jj], itb[jj] = Zr[0], itr[0]
+    tok = [l.split() for l in r.stdout.splitlines()]
+    B = {(int(t[1]), int(t[2])): int(t[3]) for t in tok if t[0] == "B"}
+    assert len(B) == lx * ly and all(B[(jj, k)] == itb[jj, k] for jj in range(ly) for k in range(lx))
+    Zo, yo = po.unmirror(Zb, y, 2)
+    Zo = np.clip(Zo, 1e-2, np.inf)
+    Pm = np.zeros_like(Zo)
+    for t in tok:
+        if t[0] == "P":
+            Pm[int(t[1]), int(t[2])] = float(t[3])
+    assert np.allclose(Pm, Zo, rtol=RTOL, atol=0) and np.array_equal(Pm == 1e-2, Zo == 1e-2)
+    Y = np.array([float(t[2]) for t in tok if t[0] == "Y"])
+    assert np.array_equal(Y, yo)
+    S = [t for t in tok if t[0] == "S"][0]
+    assert float(S[1]) == Pm.min() and float(S[2]) == Pm.max()
+    M = [t for t in tok if t[0] == "M"][0]
+    Zm, qm, lm = po.psmode_inv_lanczos(T, q0, 0.3 + 0.4j, 1e-10, 60)
+    V = np.array([float(t[2]) + 1j * float(t[3]) for t in tok if t[0] == "V"])
+    assert int(M[3]) == 0 and int(M[2]) == lm and abs(float(M[1]) - Zm) <= 1e-8 * Zm
+    ph = np.vdot(qm, V) / abs(np.vdot(qm, V))
+    assert np.linalg.norm(V - ph * qm) <= 1e-6 * np.linalg.norm(qm)
