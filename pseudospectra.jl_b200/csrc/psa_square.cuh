@@ -6,6 +6,8 @@
 // are a dense contraction (complex GEMM as 4 real DMMA per 8x8x4 block); only the 16x16 diagonal blocks are
 // per-shift.  See DESIGN.md for the layout and the step schedule.
 #pragma once
+#include <cstring>
+
 #include "psa_common.cuh"
 
 namespace psa {
@@ -388,6 +390,252 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 4) solve_kernel(SolveParams P) 
 #endif
 }
 
+// ---- the decoupled ("deep ring") solve kernel ----------------------------------------------------------------
+// Same arithmetic, same step order and therefore bit-identical results as solve_kernel, different choreography:
+//   * at most 2 CTAs per SM, so each CTA affords a ring of S = 4..6 stages (solve_kernel: 2) and 255 registers;
+//   * no CTA-wide barrier per step.  A warp that has finished a step releases the stage on a per-stage "empty"
+//     mbarrier (4 arrivals) and moves on; the loads of step q are issued (by every thread, its share of the rows)
+//     once step q - S has been released by all four warps, LOOK = S - SLACK steps ahead of the consumer, so warps may
+//     drift SLACK steps apart and a load has LOOK step times to arrive (solve_kernel: 1);
+//   * the right-hand side rows of a diagonal step arrive with the stage (they replace the unused X tile) instead of
+//     being fetched from global memory inside the serial part of the step;
+//   * loads are only issued once the step that PRODUCES their data has been completed (dep_step): with a deep ring the
+//     first block rows of a phase, and the hand-over of w from the adjoint to the plain solve, are closer than S steps.
+// Only the diagonal steps (3 % of the steps at n = 4000) still synchronise the CTA.
+template <int NSV, int S>
+__host__ __device__ constexpr int deep_smem() { return S * stage_bytes(NSV) + 128 + NSV * 16 + NSV * 8 * 2; }
+
+template <int NSV, int S, int SLACK>
+__global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_deep_kernel(SolveParams P) {
+  static_assert(S >= 3 && S <= 8 && SLACK >= 1 && SLACK < S, "ring geometry");
+  constexpr int NT = NSV / 8;
+  constexpr int STAGE_BYTES = stage_bytes(NSV);
+  constexpr int LOOK = S - SLACK;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int n_active = *P.n_active;
+  const int panel = blockIdx.x;
+  if (panel * NSV >= n_active) return;
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * STAGE_BYTES);  // 128 B reserved: full[S], empty[S]
+  uint64_t* empty_bar = full_bar + S;
+  double2* zsh = reinterpret_cast<double2*>(smem + S * STAGE_BYTES + 128);
+  double2** wptr = reinterpret_cast<double2**>(zsh + NSV);
+  const double2** qptr = (const double2**)(wptr + NSV);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp;
+
+  if (tid < NSV) {
+    const int slot = P.active[panel * NSV + tid];
+    wptr[tid] = P.Wv + (size_t)slot * P.n_pad;
+    qptr[tid] = P.iter[slot] == 0 ? P.q0 + (size_t)P.batch[slot] * P.n_pad
+                                  : (P.sel[slot] ? P.Q1 : P.Q0) + (size_t)slot * P.n_pad;
+    zsh[tid] = P.z[slot];
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1 + SOLVE_THREADS);  // thread 0 expect_tx + one cp.async arrival per thread
+      mbar_init(&empty_bar[s], SOLVE_THREADS / 32);  // one arrival per warp
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int nblk = P.nblk, n_pad = P.n_pad, n = P.n;
+  const int steps_per_phase = (int)tiles_per_phase(nblk);
+  const int total_steps = 2 * steps_per_phase;
+
+  const uint64_t pol_T = l2_policy_evict_last(), pol_X = l2_policy_evict_first();
+  auto issue = [&](const StepCursor& pc, int stage) {
+    unsigned char* sb = smem + stage * STAGE_BYTES;
+    const bool gemm = pc.c < CPB * pc.I;
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&full_bar[stage], TILE_BYTES);
+      const double2* src = (pc.phase ? P.packB : P.packA) + tile_index(pc.I, pc.c) * TILE_ELEMS;
+      bulk_g2s_hint(sb, src, TILE_BYTES, &full_bar[stage], pol_T);
+    }
+    // GEMM step: the X chunk (w resp. v, being produced in place in Wv).  Diagonal step: the right-hand side rows
+    // (q for the adjoint solve, w for the plain one).
+    const bool from_q = !gemm && pc.phase == 0;
+    const int mem0 = pc.phase ? n_pad - KC * pc.c - KC : KC * pc.c;
+#pragma unroll
+    for (int seg = tid; seg < NSV * KC; seg += SOLVE_THREADS) {  // 16-byte segments: row = seg / KC
+      const int s = seg / KC, part = seg % KC;
+      const double2* src = (from_q ? qptr[s] : (const double2*)wptr[s]) + mem0 + part;
+      cp_async16_hint(sb + TILE_BYTES + s * XROW_BYTES + part * 16, src, pol_X);
+    }
+    cp_async_mbar_arrive_noinc(&full_bar[stage]);
+  };
+  // index (over both phases) of the step whose completion makes the data loaded by step pc final; -1: input data
+  auto dep_step = [&](const StepCursor& pc) -> int {
+    if (pc.c < CPB * pc.I) return pc.phase * steps_per_phase + (int)tile_index(pc.c >> 2, pc.c);
+    if (pc.phase == 0) return -1;
+    const int cA = CPB * nblk - 1 - pc.c;  // the adjoint-phase chunk that wrote this part of w
+    return (int)tile_index(cA >> 2, cA);
+  };
+
+  double cre[2][NT][2], cim[2][NT][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < NT; ++b) cre[a][b][0] = cre[a][b][1] = cim[a][b][0] = cim[a][b][1] = 0.0;
+
+  auto gemm_step = [&](const unsigned char* sb, int flip) {
+    const double2* At = reinterpret_cast<const double2*>(sb);
+    const unsigned char* Xt = sb + TILE_BYTES + (lane >> 2) * XROW_BYTES;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double2 a[2], b[NT];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) a[mt] = At[(j * 8 + 2 * wm + mt) * 32 + lane];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+        b[nt] = *reinterpret_cast<const double2*>(Xt + nt * 8 * XROW_BYTES + (((4 * j + (lane & 3)) ^ flip) << 4));
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma884(cre[mt][nt][0], cre[mt][nt][1], a[mt].x, b[nt].x);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma884(cim[mt][nt][0], cim[mt][nt][1], a[mt].x, b[nt].y);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const double nai = -a[mt].y;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma884(cre[mt][nt][0], cre[mt][nt][1], nai, b[nt].y);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma884(cim[mt][nt][0], cim[mt][nt][1], a[mt].y, b[nt].x);
+    }
+  };
+
+  StepCursor cons{0, 0, 0}, prod{0, 0, 0};
+  int issued = 0;
+  // issue every step that is within LOOK of the consumer, whose producer step is complete and whose stage is free
+  auto pump = [&](int t_done) {
+    while (issued < total_steps && issued <= t_done + LOOK) {
+      if (dep_step(prod) > t_done) break;
+      if (issued >= S) mbar_wait(&empty_bar[issued % S], (uint32_t)(issued / S - 1) & 1u);
+      issue(prod, issued % S);
+      prod.advance();
+      if (prod.I == nblk) prod = StepCursor{1, 0, 0};
+      ++issued;
+    }
+  };
+  pump(-1);
+
+#ifdef PSA_TIMING
+  long long tm_wait = 0, tm_gemm = 0, tm_diag = 0, tm_sync = 0, tm0;
+#endif
+  for (int t = 0; t < total_steps; ++t) {
+    const int stage = t % S;
+    unsigned char* sb = smem + stage * STAGE_BYTES;
+    const int flip = cons.phase ? (KC - 1) : 0;
+    PSA_T0();
+    mbar_wait(&full_bar[stage], (uint32_t)(t / S) & 1u);
+    PSA_T1(tm_wait);
+
+    if (cons.c < CPB * cons.I) {
+      PSA_T0();
+      gemm_step(sb, flip);
+      PSA_T1(tm_gemm);
+    } else {
+      PSA_T0();
+      const int cp = cons.c - CPB * cons.I;  // diagonal sub-chunk 0..3
+      unsigned char* Xt = sb + TILE_BYTES;   // holds the right-hand side rows: element (row r, shift sl) at Xt[sl][r ^ flip]
+      if (wm == cp) {
+        // this warp owns rows 16cp..16cp+15 of the block row: turn the right-hand side into rhs - acc in place
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int r = 8 * mt + (lane >> 2), sl = 8 * nt + 2 * (lane & 3) + e;
+              double2* pb = reinterpret_cast<double2*>(Xt + sl * XROW_BYTES + ((r ^ flip) << 4));
+              const double2 g = *pb;
+              *pb = make_double2(g.x - cre[mt][nt][e], g.y - cim[mt][nt][e]);
+              cre[mt][nt][e] = 0.0;
+              cim[mt][nt][e] = 0.0;
+            }
+      }
+      __syncthreads();
+      {
+        constexpr int GROUPS = SOLVE_THREADS / 4;
+        const int grp = tid >> 2, pl = lane & 3;
+        const bool solver = grp < NSV;
+        const int s = solver ? grp : 0;
+        static_assert(NSV <= GROUPS, "one 4-lane group per shift");
+        const int mem0 = cons.phase ? n_pad - KC * cons.c - KC : KC * cons.c;
+        double2* xrow = reinterpret_cast<double2*>(Xt + s * XROW_BYTES);
+        const double2* At = reinterpret_cast<const double2*>(sb);
+        double2 zt = zsh[s];
+        if (cons.phase == 0) zt.y = -zt.y;  // adjoint system: diagonal conj(t_ii - z)
+        const int p0 = MB * cons.I + KC * cp;
+        double2 b[4], dinv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = 4 * i + pl, m = KC * cp + r;
+          b[i] = xrow[r ^ flip];
+          double2 d = At[((r >> 2) * 8 + (m >> 3)) * 32 + (m & 7) * 4 + (r & 3)];
+          d.x -= zt.x;
+          d.y -= zt.y;
+          const double inv = __drcp_rn(fma(d.x, d.x, d.y * d.y));
+          dinv[i] = make_double2(d.x * inv, -d.y * inv);
+        }
+#pragma unroll
+        for (int r = 0; r < KC; ++r) {  // forward substitution in processing order; pivot r lives on lane r & 3
+          const int ir = r >> 2, pr = r & 3;
+          double2 x = cmul(b[ir], dinv[ir]);
+          const int op = cons.phase ? n_pad - 1 - (p0 + r) : p0 + r;
+          if (op >= n) x = make_double2(0.0, 0.0);
+          if (pl == pr) b[ir] = x;
+          const int src = (lane & ~3) | pr;
+          x.x = __shfl_sync(0xffffffffu, x.x, src);
+          x.y = __shfl_sync(0xffffffffu, x.y, src);
+#pragma unroll
+          for (int i = ir; i < 4; ++i) {
+            const int r2 = 4 * i + pl;
+            if (r2 > r) {
+              const int m2 = KC * cp + r2;
+              const double2 l = At[((r >> 2) * 8 + (m2 >> 3)) * 32 + (m2 & 7) * 4 + (r & 3)];
+              cmsub(b[i], l, x);
+            }
+          }
+        }
+        if (solver) {
+          double2* op_ = wptr[s] + mem0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = 4 * i + pl;
+            xrow[r ^ flip] = b[i];
+            op_[r ^ flip] = b[i];
+          }
+        }
+      }
+      __syncthreads();  // x is in shared memory (this step's X tile) and on its way to global memory
+      if (wm > cp) gemm_step(sb, flip);
+      PSA_T1(tm_diag);
+    }
+    PSA_T0();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);  // this warp is done with the stage
+    pump(t);
+    PSA_T1(tm_sync);
+    cons.advance();
+    if (cons.I == nblk) cons = StepCursor{1, 0, 0};
+  }
+#ifdef PSA_TIMING
+  if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+    printf("[timing deep] cta %d warp %d: load-wait %lld gemm %lld diag %lld release+issue %lld clk, %d steps\n", (int)blockIdx.x,
+           warp, tm_wait, tm_gemm, tm_diag, tm_sync, total_steps);
+#endif
+}
+
 // ---- scheduler: refill idle slots from the point queue, compact the active list -------------------------
 struct SchedParams {
   int W;              // slot capacity (scratch slot has id W)
@@ -760,18 +1008,47 @@ inline int pick_panel_width(int n_active, int num_sms) {
   return best;
 }
 
+// ring geometry of the deep variant per panel width (shared memory for 2 CTAs per SM)
+constexpr int DEEP_S32 = 4, DEEP_S16 = 5, DEEP_S8 = 6, DEEP_SLACK = 2;
+
 inline int solve_set_attrs() {
-  cudaError_t e = cudaFuncSetAttribute(solve_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem(32));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem(16));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem(8));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaError_t e = cudaSuccess;
+  auto set = [&](auto* k, int bytes) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  };
+  set(solve_kernel<32>, solve_smem(32));
+  set(solve_kernel<16>, solve_smem(16));
+  set(solve_kernel<8>, solve_smem(8));
+  set(solve_deep_kernel<32, DEEP_S32, DEEP_SLACK>, deep_smem<32, DEEP_S32>());
+  set(solve_deep_kernel<16, DEEP_S16, DEEP_SLACK>, deep_smem<16, DEEP_S16>());
+  set(solve_deep_kernel<8, DEEP_S8, DEEP_SLACK>, deep_smem<8, DEEP_S8>());
   return e == cudaSuccess ? 0 : -1;
+}
+
+inline int solve_flavor() {  // experiments: PSA_SOLVE_FLAVOR=shallow|deep|auto (read at every launch)
+  const char* e = getenv("PSA_SOLVE_FLAVOR");
+  if (!e) return 2;
+  return !strcmp(e, "shallow") ? 0 : !strcmp(e, "deep") ? 1 : 2;
 }
 
 // n_active is an upper bound of the device-side count (panels past it exit at once)
 inline void launch_solve(const SolveParams& sp, int n_active, int num_sms, cudaStream_t stream) {
+  const int flavor = solve_flavor();
+  const bool deep = flavor == 1 || (flavor == 2 && false);
+  if (deep) {
+    const char* env = getenv("PSA_PANEL_WIDTH");
+    int width = env ? atoi(env) : 0;
+    if (width != 32 && width != 16 && width != 8)
+      width = n_active > 2 * num_sms * 16 ? 32 : (n_active > 2 * num_sms * 8 ? 16 : 8);
+    const int panels = (n_active + width - 1) / width;
+    switch (width) {
+      case 32: solve_deep_kernel<32, DEEP_S32, DEEP_SLACK><<<panels, SOLVE_THREADS, deep_smem<32, DEEP_S32>(), stream>>>(sp); break;
+      case 16: solve_deep_kernel<16, DEEP_S16, DEEP_SLACK><<<panels, SOLVE_THREADS, deep_smem<16, DEEP_S16>(), stream>>>(sp); break;
+      default: solve_deep_kernel<8, DEEP_S8, DEEP_SLACK><<<panels, SOLVE_THREADS, deep_smem<8, DEEP_S8>(), stream>>>(sp); break;
+    }
+    return;
+  }
   const int width = pick_panel_width(n_active, num_sms);
   const int panels = (n_active + width - 1) / width;
   switch (width) {

@@ -2,6 +2,7 @@
 identical (T, x, y, q0) and against the committed golden vectors.  Tolerance: sigma_min within 1e-6 relative of the
 oracle (north_star); iteration counts identical up to rounding-level ties at the stopping threshold."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -107,7 +108,7 @@ def test_projection_option_through_psa_compute(pkg):
     Z, x, y, levels, err, Tproj, eigAproj, algo = out
     k = Tproj.shape[0]
     assert 55 <= k < 200 and len(eigAproj) == k and algo == "sq_lanc"
-    qk = q0[:k] / np.linalg.norm(q0[:k])
+    qk = q0[:k]  # `q = q0[1:n]` (compute.jl:622): truncated, not renormalised
     Zc, _, _ = co.grid(Tproj, x, y, qk, nthreads=4)
     assert _rel(Z, np.clip(Zc, po.PS_TINY, np.inf), _floor(Tproj)) < RTOL
 
@@ -438,9 +439,9 @@ def test_maxit_above_126_and_fallback_counts(gpu):
     q0 = po.start_vector(120, 0)
     gpu.set_matrix(T)
     x, y = np.linspace(-9, 9, 6), np.linspace(-9, 9, 5)
-    Z, it, counts, _ = gpu.grid(x, y, q0, tol=1e-15, maxit=150)  # unreachable tolerance: every point runs 150 iterations
-    Zc, itc, flc = co.grid(T, x, y, q0, tol=1e-15, maxit=150)
-    assert it.max() > 126 and np.array_equal(it, itc) and _rel(Z, Zc) < RTOL and counts[0] == (flc & 1).sum()
+    Z, it, counts, _ = gpu.grid(x, y, q0, tol=0.0, maxit=150)  # `resid < 0` never holds: every point runs 150 iterations
+    Zc, itc, flc = co.grid(T, x, y, q0, tol=0.0, maxit=150)
+    assert it.min() == 150 and np.array_equal(it, itc) and _rel(Z, Zc) < RTOL and counts[0] == (flc & 1).sum() == 30
     Tg, _ = po.complex_schur(po.grcar(400))
     gpu.set_matrix(Tg)
     Z, it, counts, _ = gpu.grid(np.linspace(0.2, 2.0, 10), np.linspace(0.1, 2.5, 9), po.start_vector(400, 0))
@@ -511,3 +512,58 @@ def test_plain_c_driver_full_boundary(pkg, tmp_path):
     assert int(M[3]) == 0 and int(M[2]) == lm and abs(float(M[1]) - Zm) <= 1e-8 * Zm
     ph = np.vdot(qm, V) / abs(np.vdot(qm, V))
     assert np.linalg.norm(V - ph * qm) <= 1e-6 * np.linalg.norm(qm)
+
+
+# ---- round 2: parity at the sizes of the BASELINE configs -----------------------------------------------------------
+
+def test_c2_grcar1000_mirror_vs_oracle(pkg, gpu):
+    """BASELINE config 2: Grcar n = 1000 Schur factor, 200x200 grid with the real-matrix mirror, through psa_compute;
+    every 9th computed row (about 2400 points) against the oracle, incl. the overflow points (bigsigma -> ps_tiny)."""
+    T, eigA = po.complex_schur(po.grcar(1000))
+    ax = po.vec2ax(eigA)
+    q0 = po.start_vector(1000, 0)
+    Z, x, y, levels, err, Tp, ep, algo = pkg.psa_compute(T, 200, ax, eigA, {"real_matrix": True}, q0=q0, ctx=gpu)
+    xo, yo, nm = po.make_grid(ax, 200, True)
+    assert algo == "sq_lanc" and Z.shape == (200, 200) and np.array_equal(x, xo) and nm != 0
+    rows = np.arange(0, len(yo), 9)
+    Zc, itc, flc = co.grid(T, xo, yo[rows], q0, nthreads=os.cpu_count() or 8)
+    Zfull_o, yfull_o = po.unmirror(np.zeros((len(yo), len(xo))), yo, nm)
+    assert np.array_equal(y, yfull_o)
+    off = len(yfull_o) - len(yo) if nm > 0 else 0  # computed rows sit after the mirrored ones (top half is master)
+    Zg = Z[off + rows] if nm > 0 else Z[rows]
+    Zc = np.clip(Zc, po.PS_TINY, np.inf)
+    floor = _floor(T)
+    assert (Zc > floor).sum() > 500
+    assert _rel(Zg, Zc, floor) < RTOL
+    assert np.array_equal(Zg <= po.PS_TINY, (flc & 2) != 0)  # the same points fall back to bigsigma on both sides
+
+
+def test_n4000_slice_vs_oracle_and_svd(gpu):
+    """The headline size (BASELINE config 3, n = 4000).  T is a synthetic Schur factor with the statistics of the
+    Ginibre ensemble's (strictly upper part iid complex Gaussian, eigenvalues in the disc of radius sqrt(2n)), so no
+    O(n^3) host reduction is needed inside the test; bench.py checks the real Schur factor the same way every run.
+    80 points against the oracle, 8 of them against dense svdvals (the reference's SVD-branch quantity)."""
+    n = 4000
+    rng = np.random.default_rng(42)
+    T = np.triu(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)), 1)
+    rad = np.sqrt(2 * n) * np.sqrt(rng.random(n))
+    T[np.arange(n), np.arange(n)] = rad * np.exp(2j * np.pi * rng.random(n))
+    T = np.asfortranarray(T)
+    q0 = po.start_vector(n, 0)
+    x = np.linspace(-140.0, 140.0, 10)
+    y = np.linspace(-135.0, 135.0, 8)
+    gpu.set_matrix(T)
+    Z, it, counts, algo = gpu.grid(x, y, q0)
+    Zc, itc, flc = co.grid(T, x, y, q0, nthreads=os.cpu_count() or 8)
+    floor = _floor(T)
+    assert algo == "sq_lanc" and counts[3] == 80
+    assert (Zc > floor).sum() >= 64 and _rel(Z, Zc, floor) < RTOL
+    assert np.mean(it == itc) >= 0.97
+    checked = 0
+    for (j, k) in [(0, 0), (7, 9), (0, 9), (7, 0), (3, 0), (4, 9), (0, 4), (7, 5)]:  # far-field points: well-conditioned
+        s = po.sigmin_svd(T, x[k] + 1j * y[j])
+        if s > floor:
+            assert abs(Z[j, k] - s) / s <= abs(Zc[j, k] - s) / s * 1.01 + 1e-9  # no worse than the reference algorithm
+            assert abs(Z[j, k] - s) / s < 1e-3
+            checked += 1
+    assert checked >= 8
