@@ -480,6 +480,22 @@ def convdiff_fd(N: int):
     return (sp.kron(sp.identity(n2), A1) + sp.kron(A2, sp.identity(n1))).tocsr()
 
 
+def landau_fox_li(N: int, F: float = 0) -> np.ndarray:
+    """examples/demo_mtx.jl:260-280: Landau's discretisation of the Fox-Li laser-cavity operator (Gauss-Legendre nodes
+    and weights from the Jacobi matrix); the input of the reference's test/medcplx.jl (N = 225, F = 16)."""
+    if F == 0:
+        F = 32 if N > 200 else 12
+    k = np.arange(1, N)
+    beta = 0.5 * (1 - (2.0 * k) ** (-2.0)) ** (-0.5)
+    d, V = np.linalg.eigh(np.diag(beta, 1) + np.diag(beta, -1))
+    idx = np.argsort(d)
+    nodes = d[idx]
+    w = 2 * V[0, idx] ** 2
+    B = w[None, :] * np.sqrt(F * 1j) * np.exp(-1j * np.pi * F * (nodes[:, None] - nodes[None, :]) ** 2)
+    sw = np.sqrt(w)
+    return (sw[:, None] * B) / sw[None, :]
+
+
 def toeplitz_from_symbol(vc, vr, n: int) -> np.ndarray:
     """Banded Toeplitz matrix with first column `vc` and first row `vr` (examples/toeplitz.jl:45-67:
     vc/vr hold the coefficients, x^0 terms equal)."""

@@ -392,25 +392,30 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 4) solve_kernel(SolveParams P) 
 
 // ---- the decoupled ("deep ring") solve kernel ----------------------------------------------------------------
 // Same arithmetic, same step order and therefore bit-identical results as solve_kernel, different choreography:
-//   * at most 2 CTAs per SM, so each CTA affords a ring of S = 4..6 stages (solve_kernel: 2) and 255 registers;
-//   * no CTA-wide barrier per step.  A warp that has finished a step releases the stage on a per-stage "empty"
-//     mbarrier (4 arrivals) and moves on; the loads of step q are issued (by every thread, its share of the rows)
-//     once step q - S has been released by all four warps, LOOK = S - SLACK steps ahead of the consumer, so warps may
-//     drift SLACK steps apart and a load has LOOK step times to arrive (solve_kernel: 1);
+//   * at most 2 CTAs per SM, so each CTA affords a ring of S = 4..6 stages (solve_kernel: 2) and ~200 registers;
+//   * a fifth warp is the PRODUCER: it alone issues the loads (one bulk copy for the T tile, its lanes' share of
+//     16-byte cp.async copies for the X rows), so the four consumer warps spend their issue slots on DMMAs only;
+//   * no CTA-wide barrier per step: a consumer warp that has finished a step releases the stage on a per-stage
+//     "empty" mbarrier (4 arrivals) and moves on; the producer refills a stage once all four warps released it, up to
+//     S steps ahead, so consumer warps may drift apart by a whole ring;
 //   * the right-hand side rows of a diagonal step arrive with the stage (they replace the unused X tile) instead of
 //     being fetched from global memory inside the serial part of the step;
-//   * loads are only issued once the step that PRODUCES their data has been completed (dep_step): with a deep ring the
-//     first block rows of a phase, and the hand-over of w from the adjoint to the plain solve, are closer than S steps.
-// Only the diagonal steps (3 % of the steps at n = 4000) still synchronise the CTA.
+//   * a load is only issued once the step that PRODUCES its data has been released by all consumers (dep_step): with
+//     a deep ring the first block rows of a phase, and the hand-over of w from the adjoint to the plain solve, are
+//     closer than S steps.
+// Only the diagonal steps (3 % of the steps at n = 4000) still synchronise the four consumer warps (named barrier 1).
+constexpr int DEEP_THREADS = SOLVE_THREADS + 32;
+
 template <int NSV, int S>
 __host__ __device__ constexpr int deep_smem() { return S * stage_bytes(NSV) + 128 + NSV * 16 + NSV * 8 * 2; }
 
-template <int NSV, int S, int SLACK>
-__global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_deep_kernel(SolveParams P) {
-  static_assert(S >= 3 && S <= 8 && SLACK >= 1 && SLACK < S, "ring geometry");
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SOLVE_THREADS) : "memory"); }
+
+template <int NSV, int S>
+__global__ void __launch_bounds__(DEEP_THREADS, 2) solve_deep_kernel(SolveParams P) {
+  static_assert(S >= 3 && S <= 8, "ring geometry");
   constexpr int NT = NSV / 8;
   constexpr int STAGE_BYTES = stage_bytes(NSV);
-  constexpr int LOOK = S - SLACK;
   extern __shared__ __align__(128) unsigned char smem[];
   const int n_active = *P.n_active;
   const int panel = blockIdx.x;
@@ -435,8 +440,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_deep_kernel(SolveParam
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      mbar_init(&full_bar[s], 1 + SOLVE_THREADS);  // thread 0 expect_tx + one cp.async arrival per thread
-      mbar_init(&empty_bar[s], SOLVE_THREADS / 32);  // one arrival per warp
+      mbar_init(&full_bar[s], 1 + 32);               // producer lane 0 expect_tx + one cp.async arrival per producer lane
+      mbar_init(&empty_bar[s], SOLVE_THREADS / 32);  // one arrival per consumer warp
     }
     mbar_fence_init();
   }
@@ -446,35 +451,48 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_deep_kernel(SolveParam
   const int steps_per_phase = (int)tiles_per_phase(nblk);
   const int total_steps = 2 * steps_per_phase;
 
-  const uint64_t pol_T = l2_policy_evict_last(), pol_X = l2_policy_evict_first();
-  auto issue = [&](const StepCursor& pc, int stage) {
-    unsigned char* sb = smem + stage * STAGE_BYTES;
-    const bool gemm = pc.c < CPB * pc.I;
-    if (tid == 0) {
-      mbar_arrive_expect_tx(&full_bar[stage], TILE_BYTES);
-      const double2* src = (pc.phase ? P.packB : P.packA) + tile_index(pc.I, pc.c) * TILE_ELEMS;
-      bulk_g2s_hint(sb, src, TILE_BYTES, &full_bar[stage], pol_T);
-    }
-    // GEMM step: the X chunk (w resp. v, being produced in place in Wv).  Diagonal step: the right-hand side rows
-    // (q for the adjoint solve, w for the plain one).
-    const bool from_q = !gemm && pc.phase == 0;
-    const int mem0 = pc.phase ? n_pad - KC * pc.c - KC : KC * pc.c;
+  if (warp == SOLVE_THREADS / 32) {
+    // ================= producer warp =================
+    const uint64_t pol_T = l2_policy_evict_last(), pol_X = l2_policy_evict_first();
+    StepCursor pc{0, 0, 0};
+    for (int q = 0; q < total_steps; ++q) {
+      const int stage = q % S;
+      const bool gemm = pc.c < CPB * pc.I;
+      // the stage is free once every consumer warp released step q - S
+      if (q >= S) mbar_wait(&empty_bar[stage], (uint32_t)(q / S - 1) & 1u);
+      // the data this step loads is final once the step that produced it has been released by every consumer warp:
+      //   GEMM step: X chunk c, produced by the diagonal step (c/4, c) of the same phase;
+      //   diagonal step of the plain solve: its right-hand side w, produced by the adjoint phase (mirror chunk);
+      //   diagonal step of the adjoint solve: q, an input.
+      int dep = -1;
+      if (gemm) dep = pc.phase * steps_per_phase + (int)tile_index(pc.c >> 2, pc.c);
+      else if (pc.phase == 1) {
+        const int cA = CPB * nblk - 1 - pc.c;
+        dep = (int)tile_index(cA >> 2, cA);
+      }
+      if (dep >= 0 && dep > q - S) mbar_wait(&empty_bar[dep % S], (uint32_t)(dep / S) & 1u);  // (older steps: implied by the wait above)
+      unsigned char* sb = smem + stage * STAGE_BYTES;
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full_bar[stage], TILE_BYTES);
+        const double2* src = (pc.phase ? P.packB : P.packA) + tile_index(pc.I, pc.c) * TILE_ELEMS;
+        bulk_g2s_hint(sb, src, TILE_BYTES, &full_bar[stage], pol_T);
+      }
+      const bool from_q = !gemm && pc.phase == 0;
+      const int mem0 = pc.phase ? n_pad - KC * pc.c - KC : KC * pc.c;
 #pragma unroll
-    for (int seg = tid; seg < NSV * KC; seg += SOLVE_THREADS) {  // 16-byte segments: row = seg / KC
-      const int s = seg / KC, part = seg % KC;
-      const double2* src = (from_q ? qptr[s] : (const double2*)wptr[s]) + mem0 + part;
-      cp_async16_hint(sb + TILE_BYTES + s * XROW_BYTES + part * 16, src, pol_X);
+      for (int seg = lane; seg < NSV * KC; seg += 32) {  // 16-byte segments: row = seg / KC
+        const int s = seg / KC, part = seg % KC;
+        const double2* src = (from_q ? qptr[s] : (const double2*)wptr[s]) + mem0 + part;
+        cp_async16_hint(sb + TILE_BYTES + s * XROW_BYTES + part * 16, src, pol_X);
+      }
+      cp_async_mbar_arrive_noinc(&full_bar[stage]);
+      pc.advance();
+      if (pc.I == nblk) pc = StepCursor{1, 0, 0};
     }
-    cp_async_mbar_arrive_noinc(&full_bar[stage]);
-  };
-  // index (over both phases) of the step whose completion makes the data loaded by step pc final; -1: input data
-  auto dep_step = [&](const StepCursor& pc) -> int {
-    if (pc.c < CPB * pc.I) return pc.phase * steps_per_phase + (int)tile_index(pc.c >> 2, pc.c);
-    if (pc.phase == 0) return -1;
-    const int cA = CPB * nblk - 1 - pc.c;  // the adjoint-phase chunk that wrote this part of w
-    return (int)tile_index(cA >> 2, cA);
-  };
+    return;
+  }
 
+  // ================= consumer warps =================
   double cre[2][NT][2], cim[2][NT][2];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
@@ -513,21 +531,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_deep_kernel(SolveParam
     }
   };
 
-  StepCursor cons{0, 0, 0}, prod{0, 0, 0};
-  int issued = 0;
-  // issue every step that is within LOOK of the consumer, whose producer step is complete and whose stage is free
-  auto pump = [&](int t_done) {
-    while (issued < total_steps && issued <= t_done + LOOK) {
-      if (dep_step(prod) > t_done) break;
-      if (issued >= S) mbar_wait(&empty_bar[issued % S], (uint32_t)(issued / S - 1) & 1u);
-      issue(prod, issued % S);
-      prod.advance();
-      if (prod.I == nblk) prod = StepCursor{1, 0, 0};
-      ++issued;
-    }
-  };
-  pump(-1);
-
+  StepCursor cons{0, 0, 0};
 #ifdef PSA_TIMING
   long long tm_wait = 0, tm_gemm = 0, tm_diag = 0, tm_sync = 0, tm0;
 #endif
@@ -563,7 +567,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_deep_kernel(SolveParam
               cim[mt][nt][e] = 0.0;
             }
       }
-      __syncthreads();
+      consumer_sync();
       {
         constexpr int GROUPS = SOLVE_THREADS / 4;
         const int grp = tid >> 2, pl = lane & 3;
@@ -617,21 +621,20 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) solve_deep_kernel(SolveParam
           }
         }
       }
-      __syncthreads();  // x is in shared memory (this step's X tile) and on its way to global memory
+      consumer_sync();  // x is in shared memory (this step's X tile) and on its way to global memory
       if (wm > cp) gemm_step(sb, flip);
       PSA_T1(tm_diag);
     }
     PSA_T0();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[stage]);  // this warp is done with the stage
-    pump(t);
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);  // release: this warp is done with the stage (and its x is written)
     PSA_T1(tm_sync);
     cons.advance();
     if (cons.I == nblk) cons = StepCursor{1, 0, 0};
   }
 #ifdef PSA_TIMING
   if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
-    printf("[timing deep] cta %d warp %d: load-wait %lld gemm %lld diag %lld release+issue %lld clk, %d steps\n", (int)blockIdx.x,
+    printf("[timing deep] cta %d warp %d: load-wait %lld gemm %lld diag %lld release %lld clk, %d steps\n", (int)blockIdx.x,
            warp, tm_wait, tm_gemm, tm_diag, tm_sync, total_steps);
 #endif
 }
@@ -1009,7 +1012,7 @@ inline int pick_panel_width(int n_active, int num_sms) {
 }
 
 // ring geometry of the deep variant per panel width (shared memory for 2 CTAs per SM)
-constexpr int DEEP_S32 = 4, DEEP_S16 = 5, DEEP_S8 = 6, DEEP_SLACK = 2;
+constexpr int DEEP_S32 = 4, DEEP_S16 = 5, DEEP_S8 = 6;
 
 inline int solve_set_attrs() {
   cudaError_t e = cudaSuccess;
@@ -1020,9 +1023,9 @@ inline int solve_set_attrs() {
   set(solve_kernel<32>, solve_smem(32));
   set(solve_kernel<16>, solve_smem(16));
   set(solve_kernel<8>, solve_smem(8));
-  set(solve_deep_kernel<32, DEEP_S32, DEEP_SLACK>, deep_smem<32, DEEP_S32>());
-  set(solve_deep_kernel<16, DEEP_S16, DEEP_SLACK>, deep_smem<16, DEEP_S16>());
-  set(solve_deep_kernel<8, DEEP_S8, DEEP_SLACK>, deep_smem<8, DEEP_S8>());
+  set(solve_deep_kernel<32, DEEP_S32>, deep_smem<32, DEEP_S32>());
+  set(solve_deep_kernel<16, DEEP_S16>, deep_smem<16, DEEP_S16>());
+  set(solve_deep_kernel<8, DEEP_S8>, deep_smem<8, DEEP_S8>());
   return e == cudaSuccess ? 0 : -1;
 }
 
@@ -1032,20 +1035,38 @@ inline int solve_flavor() {  // experiments: PSA_SOLVE_FLAVOR=shallow|deep|auto 
   return !strcmp(e, "shallow") ? 0 : !strcmp(e, "deep") ? 1 : 2;
 }
 
-// n_active is an upper bound of the device-side count (panels past it exit at once)
+// Panel width for the deep-ring kernel (2 CTAs per SM): launch time in units of a full 32-wide round, measured on
+// B200 at n = 4000 (profiles/r02_flavor_check_v2.log): k = 1, 2 co-resident CTAs per SM.
+inline int pick_deep_width(int n_active, int num_sms) {
+  const char* env = getenv("PSA_PANEL_WIDTH");  // experiments only
+  const int forced = env ? atoi(env) : 0;
+  if (forced == 32 || forced == 16 || forced == 8) return forced;
+  static const int widths[3] = {8, 16, 32};
+  static const double cost[3][3] = {{0.0, 0.215, 0.291}, {0.0, 0.341, 0.520}, {0.0, 0.603, 1.000}};
+  int best = 32;
+  double best_cost = 1e300;
+  for (int i = 0; i < 3; ++i) {
+    const int panels = (n_active + widths[i] - 1) / widths[i];
+    const int rounds = panels / (2 * num_sms), rest = panels % (2 * num_sms);
+    const double c = rounds * cost[i][2] + (rest == 0 ? 0.0 : cost[i][rest <= num_sms ? 1 : 2]);
+    if (c < best_cost - 1e-12) {
+      best_cost = c;
+      best = widths[i];
+    }
+  }
+  return best;
+}
+
+// n_active is an upper bound of the device-side count (panels past it exit at once).  The deep-ring kernel is the
+// default; PSA_SOLVE_FLAVOR=shallow selects the round-1 choreography (same results bit for bit) for A/B timing.
 inline void launch_solve(const SolveParams& sp, int n_active, int num_sms, cudaStream_t stream) {
-  const int flavor = solve_flavor();
-  const bool deep = flavor == 1 || (flavor == 2 && false);
-  if (deep) {
-    const char* env = getenv("PSA_PANEL_WIDTH");
-    int width = env ? atoi(env) : 0;
-    if (width != 32 && width != 16 && width != 8)
-      width = n_active > 2 * num_sms * 16 ? 32 : (n_active > 2 * num_sms * 8 ? 16 : 8);
+  if (solve_flavor() != 0) {
+    const int width = pick_deep_width(n_active, num_sms);
     const int panels = (n_active + width - 1) / width;
     switch (width) {
-      case 32: solve_deep_kernel<32, DEEP_S32, DEEP_SLACK><<<panels, SOLVE_THREADS, deep_smem<32, DEEP_S32>(), stream>>>(sp); break;
-      case 16: solve_deep_kernel<16, DEEP_S16, DEEP_SLACK><<<panels, SOLVE_THREADS, deep_smem<16, DEEP_S16>(), stream>>>(sp); break;
-      default: solve_deep_kernel<8, DEEP_S8, DEEP_SLACK><<<panels, SOLVE_THREADS, deep_smem<8, DEEP_S8>(), stream>>>(sp); break;
+      case 32: solve_deep_kernel<32, DEEP_S32><<<panels, DEEP_THREADS, deep_smem<32, DEEP_S32>(), stream>>>(sp); break;
+      case 16: solve_deep_kernel<16, DEEP_S16><<<panels, DEEP_THREADS, deep_smem<16, DEEP_S16>(), stream>>>(sp); break;
+      default: solve_deep_kernel<8, DEEP_S8><<<panels, DEEP_THREADS, deep_smem<8, DEEP_S8>(), stream>>>(sp); break;
     }
     return;
   }

@@ -435,18 +435,20 @@ def test_pseudomode_through_the_c_abi(pkg, gpu):
 def test_maxit_above_126_and_fallback_counts(gpu):
     """maxit_lancs is mutable (compute.jl:27): no silent clamp.  Fallback points count as non-converged too
     (compute.jl:654-656 `break`s with lancz_converged false, so both warnings fire)."""
-    T, _ = po.complex_schur(po.random_complex(120, 5))
-    q0 = po.start_vector(120, 0)
+    T, _ = po.complex_schur(po.random_complex(400, 5))  # n > maxit: no exact Krylov breakdown before the limit
+    q0 = po.start_vector(400, 0)
     gpu.set_matrix(T)
     x, y = np.linspace(-9, 9, 6), np.linspace(-9, 9, 5)
     Z, it, counts, _ = gpu.grid(x, y, q0, tol=0.0, maxit=150)  # `resid < 0` never holds: every point runs 150 iterations
     Zc, itc, flc = co.grid(T, x, y, q0, tol=0.0, maxit=150)
     assert it.min() == 150 and np.array_equal(it, itc) and _rel(Z, Zc) < RTOL and counts[0] == (flc & 1).sum() == 30
-    Tg, _ = po.complex_schur(po.grcar(400))
-    gpu.set_matrix(Tg)
-    Z, it, counts, _ = gpu.grid(np.linspace(0.2, 2.0, 10), np.linspace(0.1, 2.5, 9), po.start_vector(400, 0))
-    Zc, itc, flc = co.grid(Tg, np.linspace(0.2, 2.0, 10), np.linspace(0.1, 2.5, 9), po.start_vector(400, 0))
-    assert counts[1] == ((flc & 2) != 0).sum() > 0 and counts[0] == ((flc & 1) != 0).sum() >= counts[1]
+    To = np.asfortranarray(np.triu(np.ones((60, 60), dtype=np.complex128)))  # z = 1 sits exactly on an eigenvalue
+    gpu.set_matrix(To)
+    xs, ys = np.array([1.0, 3.0]), np.array([0.0, 2.0])
+    Z, it, counts, _ = gpu.grid(xs, ys, po.start_vector(60, 0))
+    Zc, itc, flc = co.grid(To, xs, ys, po.start_vector(60, 0))
+    assert counts[1] == ((flc & 2) != 0).sum() == 1 and counts[0] == ((flc & 1) != 0).sum() >= 1
+    assert Z[0, 0] < po.PS_TINY and Zc[0, 0] < po.PS_TINY
 
 
 def test_zoom_reuses_the_resident_matrix(pkg, gpu):
@@ -567,3 +569,46 @@ def test_n4000_slice_vs_oracle_and_svd(gpu):
             assert abs(Z[j, k] - s) / s < 1e-3
             checked += 1
     assert checked >= 8
+
+
+# ---- the reference's own tests at this boundary, restated ----------------------------------------------------------
+
+@pytest.mark.parametrize("n", [20, 60])
+def test_reference_threads_jl(pkg, gpu, n):
+    """test/threads.jl:7-19: complex random n in {20 (SVD), 60 (sq_lanc)}, 100x100 grid on [-3,3]^2; two runs with
+    fresh random start vectors agree to norm(Z0 - Z1)/norm(Z0) < 1e-4.  Z0 = GPU psa_compute (vectors drawn per row
+    batch like compute.jl:207), Z1 = the oracle with another vector."""
+    rng = np.random.default_rng(n)
+    T, eigA = po.complex_schur(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    ax = [-3, 3, -3, 3]
+    out = pkg.psa_compute(T, 100, ax, eigA, {}, rng=np.random.default_rng(5), ctx=gpu)
+    assert out[7] == ("SVD" if n < 55 else "sq_lanc")
+    x, y, _ = po.make_grid(ax, 100, False)
+    if n < 55:
+        Z1 = np.array([[po.sigmin_svd(T, xx + 1j * yy) for xx in x] for yy in y])
+    else:
+        Z1 = co.grid(T, x, y, po.start_vector(n, 99), nthreads=os.cpu_count() or 8)[0]
+    Z1 = np.clip(Z1, po.PS_TINY, np.inf)
+    assert np.linalg.norm(out[0] - Z1) / np.linalg.norm(out[0]) < 1e-4
+
+
+def test_reference_medcplx(pkg, gpu):
+    """test/medcplx.jl:7-14: landau_fox_li(225, 16), 60x60 grid on [-1.1,1.2]x[-1.1,1.1] -> :sq_lanc; then the
+    pseudomode at z = 1im the way plotmode asks for it (tol 1e-15, 20 iterations,
+    ext/PseudospectraPlots/PseudospectraPlots.jl:221-223)."""
+    T, eigA = po.complex_schur(po.landau_fox_li(225, 16))
+    ax = [-1.1, 1.2, -1.1, 1.1]
+    q0 = po.start_vector(225, 0)
+    Z, x, y, levels, err, Tp, ep, algo = pkg.psa_compute(T, 60, ax, eigA, {"levels": np.arange(-5, -0.9, 0.5)}, q0=q0,
+                                                         ctx=gpu)
+    assert algo == "sq_lanc" and err == 0 and Z.shape == (60, 60)
+    Zc, itc, flc = co.grid(T, x, y, q0, nthreads=os.cpu_count() or 8)
+    assert _rel(Z, np.clip(Zc, po.PS_TINY, np.inf), _floor(T)) < RTOL
+    Zg, qg, l, info = gpu.pseudomode(1j, q0, 1e-15, 20)
+    Zo, qo, lo = po.psmode_inv_lanczos(T, q0, 1j, 1e-15, 20)
+    assert l == lo and abs(Zg - Zo) <= 1e-8 * Zo
+    if l < 20:
+        ph = np.vdot(qo, qg) / abs(np.vdot(qo, qg))
+        assert info == 0 and np.linalg.norm(qg - ph * qo) <= 1e-6
+    else:
+        assert info == 1  # `l >= num_its` -> the reference returns NaN (modes.jl:262-272)

@@ -175,3 +175,32 @@ def test_shift_axes_property_based():
         assert yf[0] >= lo - 1e-9 * (hi - lo) and yf[-1] <= hi + 1e-9 * (hi - lo)
 
     check()
+
+
+def test_reference_medcplx_input_selects_sq_lanc():
+    """test/medcplx.jl:7-14 restated: landau_fox_li(225, 16) is complex dense 225 x 225 -> `algo == :sq_lanc`; its
+    spectrum lies in the unit disc (Landau 1977), which pins the generator."""
+    A = po.landau_fox_li(225, 16)
+    assert A.shape == (225, 225) and np.iscomplexobj(A)
+    T, eigA = po.complex_schur(A)
+    assert np.abs(eigA).max() < 1.0 + 1e-10
+    Z, algo, _ = po.psacore(T, po.start_vector(225), np.array([0.0, 0.6]), np.array([1.0]), 1)
+    assert algo == "sq_lanc" and np.all(np.isfinite(Z))
+
+
+@pytest.mark.parametrize("n", [20, 60])
+def test_reference_threads_jl_self_consistency(n):
+    """test/threads.jl:7-19 restated: two psa_compute runs on the same Schur factor (fresh random start vectors each,
+    compute.jl:207) agree to norm(Z0 - Z1)/norm(Z0) < 1e-4 -- the ONLY numerical assertion the reference's test-suite
+    makes at this boundary.  Here: numpy restatement (per-batch vectors) vs C restatement (another vector)."""
+    rng = np.random.default_rng(n)
+    T, eigA = po.complex_schur(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    ax, npts = [-3, 3, -3, 3], 100 if n == 20 else 40  # (n = 60 on a coarser grid: the numpy loop is slow)
+    Z0 = po.psa_compute(T, npts, ax, eigA, {})[0]
+    x, y, _ = po.make_grid(ax, npts, False)
+    if n < 55:
+        Z1 = po.psacore(T, po.start_vector(n, 99), x, y, 1)[0]
+    else:
+        Z1 = co.grid(T, x, y, po.start_vector(n, 99), nthreads=4)[0]
+    Z1 = np.clip(Z1, po.PS_TINY, np.inf)
+    assert np.linalg.norm(Z0 - Z1) / np.linalg.norm(Z0) < 1e-4
