@@ -90,6 +90,7 @@ def psacore(T, S, q0, x, y, bw, *, tol=1e-5, threaded=False, nt=None, warned=Non
         _, T, U = cache
         q0 = np.asarray(q0)[..., :n] @ U.conj()  # rows are start vectors: (U' q)^T = q^T conj(U)
         m = n
+    key = _matrix_key(T, thresholds, upper_wrapper)
     if not ((resident and ctx.shape == (m, n)) or getattr(ctx, "_matrix_key", None) == key):
         ctx._matrix_key = None
         ctx.set_thresholds(thresholds.minlancs4psa, thresholds.maxstdqr4hess)

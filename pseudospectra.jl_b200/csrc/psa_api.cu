@@ -266,9 +266,13 @@ int slot_capacity(const Context* ctx, const Device& d, long long points) {
   if (is_hess_algo(ctx->algo)) {
     cap = hess_slot_capacity(ctx->n, d.num_sms);
   } else {
-    cap = 4LL * d.num_sms * NS;  // four resident solve CTAs per SM, NS shifts each
+    cap = 4LL * d.num_sms * NS;  // two rounds of two resident solve CTAs per SM, NS shifts each
   }
   long long w = std::min(cap, (points + NS - 1) / NS * NS);
+  // between one and two full rounds of panels, every tick would pay for a second, nearly empty round: keep exactly
+  // one round of slots in flight and let the remaining points wait in the queue
+  const long long round = 2LL * d.num_sms * NS;
+  if (!is_hess_algo(ctx->algo) && w > round && w < 2 * round) w = round;
   return (int)std::max<long long>(w, NS);
 }
 

@@ -404,17 +404,22 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 4) solve_kernel(SolveParams P) 
 //     a deep ring the first block rows of a phase, and the hand-over of w from the adjoint to the plain solve, are
 //     closer than S steps.
 // Only the diagonal steps (3 % of the steps at n = 4000) still synchronise the four consumer warps (named barrier 1).
-constexpr int DEEP_THREADS = SOLVE_THREADS + 32;
+// CW consumer warps (4: each owns 16 rows of the block row; 8: 8 rows each, i.e. four DMMA-issuing warps per SM
+// sub-partition at 2 CTAs per SM) + 1 producer warp.
+__host__ __device__ constexpr int deep_threads(int cw) { return cw * 32 + 32; }
 
 template <int NSV, int S>
 __host__ __device__ constexpr int deep_smem() { return S * stage_bytes(NSV) + 128 + NSV * 16 + NSV * 8 * 2; }
 
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SOLVE_THREADS) : "memory"); }
+template <int THREADS>
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 
-template <int NSV, int S>
-__global__ void __launch_bounds__(DEEP_THREADS, 2) solve_deep_kernel(SolveParams P) {
-  static_assert(S >= 3 && S <= 8, "ring geometry");
+template <int NSV, int S, int CW>
+__global__ void __launch_bounds__(deep_threads(CW), 2) solve_deep_kernel(SolveParams P) {
+  static_assert(S >= 3 && S <= 8 && (CW == 4 || CW == 8), "ring geometry");
   constexpr int NT = NSV / 8;
+  constexpr int MT = 8 / CW;              // 8-row DMMA tiles per consumer warp
+  constexpr int CTHREADS = CW * 32;       // consumer threads
   constexpr int STAGE_BYTES = stage_bytes(NSV);
   extern __shared__ __align__(128) unsigned char smem[];
   const int n_active = *P.n_active;
@@ -441,7 +446,7 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) solve_deep_kernel(SolveParams
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1 + 32);               // producer lane 0 expect_tx + one cp.async arrival per producer lane
-      mbar_init(&empty_bar[s], SOLVE_THREADS / 32);  // one arrival per consumer warp
+      mbar_init(&empty_bar[s], CW);                  // one arrival per consumer warp
     }
     mbar_fence_init();
   }
@@ -451,7 +456,7 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) solve_deep_kernel(SolveParams
   const int steps_per_phase = (int)tiles_per_phase(nblk);
   const int total_steps = 2 * steps_per_phase;
 
-  if (warp == SOLVE_THREADS / 32) {
+  if (warp == CW) {
     // ================= producer warp =================
     const uint64_t pol_T = l2_policy_evict_last(), pol_X = l2_policy_evict_first();
     StepCursor pc{0, 0, 0};
@@ -493,9 +498,9 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) solve_deep_kernel(SolveParams
   }
 
   // ================= consumer warps =================
-  double cre[2][NT][2], cim[2][NT][2];
+  double cre[MT][NT][2], cim[MT][NT][2];
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+  for (int a = 0; a < MT; ++a)
 #pragma unroll
     for (int b = 0; b < NT; ++b) cre[a][b][0] = cre[a][b][1] = cim[a][b][0] = cim[a][b][1] = 0.0;
 
@@ -504,28 +509,28 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) solve_deep_kernel(SolveParams
     const unsigned char* Xt = sb + TILE_BYTES + (lane >> 2) * XROW_BYTES;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      double2 a[2], b[NT];
+      double2 a[MT], b[NT];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) a[mt] = At[(j * 8 + 2 * wm + mt) * 32 + lane];
+      for (int mt = 0; mt < MT; ++mt) a[mt] = At[(j * 8 + MT * wm + mt) * 32 + lane];
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt)
         b[nt] = *reinterpret_cast<const double2*>(Xt + nt * 8 * XROW_BYTES + (((4 * j + (lane & 3)) ^ flip) << 4));
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) dmma884(cre[mt][nt][0], cre[mt][nt][1], a[mt].x, b[nt].x);
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) dmma884(cim[mt][nt][0], cim[mt][nt][1], a[mt].x, b[nt].y);
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
         const double nai = -a[mt].y;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) dmma884(cre[mt][nt][0], cre[mt][nt][1], nai, b[nt].y);
       }
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) dmma884(cim[mt][nt][0], cim[mt][nt][1], a[mt].y, b[nt].x);
     }
@@ -551,15 +556,15 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) solve_deep_kernel(SolveParams
       PSA_T0();
       const int cp = cons.c - CPB * cons.I;  // diagonal sub-chunk 0..3
       unsigned char* Xt = sb + TILE_BYTES;   // holds the right-hand side rows: element (row r, shift sl) at Xt[sl][r ^ flip]
-      if (wm == cp) {
-        // this warp owns rows 16cp..16cp+15 of the block row: turn the right-hand side into rhs - acc in place
+      if ((MT * wm) >> 1 == cp) {
+        // this warp owns (some of the) rows 16cp..16cp+15 of the block row: turn the right-hand side into rhs - acc
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int r = 8 * mt + (lane >> 2), sl = 8 * nt + 2 * (lane & 3) + e;
+              const int r = 8 * ((MT * wm + mt) & 1) + (lane >> 2), sl = 8 * nt + 2 * (lane & 3) + e;
               double2* pb = reinterpret_cast<double2*>(Xt + sl * XROW_BYTES + ((r ^ flip) << 4));
               const double2 g = *pb;
               *pb = make_double2(g.x - cre[mt][nt][e], g.y - cim[mt][nt][e]);
@@ -567,8 +572,8 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) solve_deep_kernel(SolveParams
               cim[mt][nt][e] = 0.0;
             }
       }
-      consumer_sync();
-      {
+      consumer_sync<CTHREADS>();
+      if (warp < SOLVE_THREADS / 32) {  // the first four warps solve (4 lanes per shift); with CW = 8 the others wait
         constexpr int GROUPS = SOLVE_THREADS / 4;
         const int grp = tid >> 2, pl = lane & 3;
         const bool solver = grp < NSV;
@@ -621,8 +626,8 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) solve_deep_kernel(SolveParams
           }
         }
       }
-      consumer_sync();  // x is in shared memory (this step's X tile) and on its way to global memory
-      if (wm > cp) gemm_step(sb, flip);
+      consumer_sync<CTHREADS>();  // x is in shared memory (this step's X tile) and on its way to global memory
+      if (MT * wm >= 2 * (cp + 1)) gemm_step(sb, flip);  // rows below the chunk
       PSA_T1(tm_diag);
     }
     PSA_T0();
@@ -1023,9 +1028,12 @@ inline int solve_set_attrs() {
   set(solve_kernel<32>, solve_smem(32));
   set(solve_kernel<16>, solve_smem(16));
   set(solve_kernel<8>, solve_smem(8));
-  set(solve_deep_kernel<32, DEEP_S32>, deep_smem<32, DEEP_S32>());
-  set(solve_deep_kernel<16, DEEP_S16>, deep_smem<16, DEEP_S16>());
-  set(solve_deep_kernel<8, DEEP_S8>, deep_smem<8, DEEP_S8>());
+  set(solve_deep_kernel<32, DEEP_S32, 4>, deep_smem<32, DEEP_S32>());
+  set(solve_deep_kernel<32, DEEP_S32, 8>, deep_smem<32, DEEP_S32>());
+  set(solve_deep_kernel<16, DEEP_S16, 4>, deep_smem<16, DEEP_S16>());
+  set(solve_deep_kernel<16, DEEP_S16, 8>, deep_smem<16, DEEP_S16>());
+  set(solve_deep_kernel<8, DEEP_S8, 4>, deep_smem<8, DEEP_S8>());
+  set(solve_deep_kernel<8, DEEP_S8, 8>, deep_smem<8, DEEP_S8>());
   return e == cudaSuccess ? 0 : -1;
 }
 
@@ -1035,14 +1043,16 @@ inline int solve_flavor() {  // experiments: PSA_SOLVE_FLAVOR=shallow|deep|auto 
   return !strcmp(e, "shallow") ? 0 : !strcmp(e, "deep") ? 1 : 2;
 }
 
-// Panel width for the deep-ring kernel (2 CTAs per SM): launch time in units of a full 32-wide round, measured on
-// B200 at n = 4000 (profiles/r02_flavor_check_v2.log): k = 1, 2 co-resident CTAs per SM.
+// Panel width for the deep-ring kernel: launch time in units of a full 32-wide round (2 CTAs per SM, 4 consumer
+// warps each), measured on B200 at n = 4000 (profiles/r02_flavor_check_v3.log).  k = 1: at most one CTA per SM, run
+// with 8 consumer warps per CTA (four DMMA-issuing warps per SM sub-partition instead of one: 6.6 ms instead of
+// 8.0 ms for a lone 8-wide panel); k = 2: two CTAs per SM with 4 consumer warps each (register budget).
 inline int pick_deep_width(int n_active, int num_sms) {
   const char* env = getenv("PSA_PANEL_WIDTH");  // experiments only
   const int forced = env ? atoi(env) : 0;
   if (forced == 32 || forced == 16 || forced == 8) return forced;
   static const int widths[3] = {8, 16, 32};
-  static const double cost[3][3] = {{0.0, 0.215, 0.291}, {0.0, 0.341, 0.520}, {0.0, 0.603, 1.000}};
+  static const double cost[3][3] = {{0.0, 0.186, 0.299}, {0.0, 0.304, 0.536}, {0.0, 0.553, 1.000}};
   int best = 32;
   double best_cost = 1e300;
   for (int i = 0; i < 3; ++i) {
@@ -1057,17 +1067,25 @@ inline int pick_deep_width(int n_active, int num_sms) {
   return best;
 }
 
+template <int CW>
+inline void launch_deep(const SolveParams& sp, int width, int panels, cudaStream_t stream) {
+  switch (width) {
+    case 32: solve_deep_kernel<32, DEEP_S32, CW><<<panels, deep_threads(CW), deep_smem<32, DEEP_S32>(), stream>>>(sp); break;
+    case 16: solve_deep_kernel<16, DEEP_S16, CW><<<panels, deep_threads(CW), deep_smem<16, DEEP_S16>(), stream>>>(sp); break;
+    default: solve_deep_kernel<8, DEEP_S8, CW><<<panels, deep_threads(CW), deep_smem<8, DEEP_S8>(), stream>>>(sp); break;
+  }
+}
+
 // n_active is an upper bound of the device-side count (panels past it exit at once).  The deep-ring kernel is the
 // default; PSA_SOLVE_FLAVOR=shallow selects the round-1 choreography (same results bit for bit) for A/B timing.
 inline void launch_solve(const SolveParams& sp, int n_active, int num_sms, cudaStream_t stream) {
   if (solve_flavor() != 0) {
     const int width = pick_deep_width(n_active, num_sms);
     const int panels = (n_active + width - 1) / width;
-    switch (width) {
-      case 32: solve_deep_kernel<32, DEEP_S32><<<panels, DEEP_THREADS, deep_smem<32, DEEP_S32>(), stream>>>(sp); break;
-      case 16: solve_deep_kernel<16, DEEP_S16><<<panels, DEEP_THREADS, deep_smem<16, DEEP_S16>(), stream>>>(sp); break;
-      default: solve_deep_kernel<8, DEEP_S8><<<panels, DEEP_THREADS, deep_smem<8, DEEP_S8>(), stream>>>(sp); break;
-    }
+    const char* ecw = getenv("PSA_DEEP_CW");  // experiments only
+    const int cw = ecw ? atoi(ecw) : (panels <= num_sms ? 8 : 4);
+    if (cw == 4) launch_deep<4>(sp, width, panels, stream);
+    else launch_deep<8>(sp, width, panels, stream);
     return;
   }
   const int width = pick_panel_width(n_active, num_sms);

@@ -608,11 +608,13 @@ def test_reference_medcplx(pkg, gpu):
     assert _rel(Z, np.clip(Zc, po.PS_TINY, np.inf), _floor(T)) < RTOL
     Zg, qg, l, info = gpu.pseudomode(1j, q0, 1e-15, 20)
     Zo, qo, lo = po.psmode_inv_lanczos(T, q0, 1j, 1e-15, 20)
-    assert l == lo and abs(Zg - Zo) <= 1e-8 * Zo
-    if l < 20:
+    # tol = 1e-15 asks for agreement of successive Ritz values to the last bit, so WHEN the test fires is decided by
+    # rounding: the iteration counts may differ by a step or two, the converged value may not
+    assert abs(l - lo) <= 2 and abs(Zg - Zo) <= 1e-8 * Zo
+    if l < 20 and lo < 20:
         ph = np.vdot(qo, qg) / abs(np.vdot(qo, qg))
         assert info == 0 and np.linalg.norm(qg - ph * qo) <= 1e-6
-    else:
+    elif l >= 20:
         assert info == 1  # `l >= num_its` -> the reference returns NaN (modes.jl:262-272)
 
 

@@ -9,6 +9,9 @@ P = psa_b200_loader.load_package()
 import psa_oracle as po, c_oracle as co
 
 def flavor(f, w=None):
+    if f.startswith("deep") and len(f) > 4:
+        os.environ["PSA_DEEP_CW"] = f[4:]
+        f = "deep"
     os.environ["PSA_SOLVE_FLAVOR"] = f
     if w: os.environ["PSA_PANEL_WIDTH"] = str(w)
     else: os.environ.pop("PSA_PANEL_WIDTH", None)
@@ -23,15 +26,16 @@ for n, ns in ((64, 1), (150, 70), (333, 130), (1000, 300)):
     g.set_matrix(T)
     flavor("shallow"); V0 = g.apply_resolvent(z, Q)
     for w in (8, 16, 32):
-        flavor("deep", w); V1 = g.apply_resolvent(z, Q)
-        same = np.array_equal(V0, V1)
-        ok &= same
-        print(f"apply n={n} ns={ns} deep width {w}: bitwise equal {same}", flush=True)
+        for f in ("deep4", "deep8"):
+            flavor(f, w); V1 = g.apply_resolvent(z, Q)
+            same = np.array_equal(V0, V1)
+            ok &= same
+            print(f"apply n={n} ns={ns} {f} width {w}: bitwise equal {same}", flush=True)
 T, eigA = po.complex_schur(po.readme_matrix(150))
 x, y, _ = po.make_grid(po.vec2ax(eigA), 100, False)
 q0 = po.start_vector(150, 0)
 g.set_matrix(T)
-for f in ("shallow", "deep"):
+for f in ("shallow", "deep4", "deep8"):
     flavor(f)
     g.grid(x, y, q0)
     t0 = time.time(); Z, it, c, _ = g.grid(x, y, q0); dt = time.time() - t0
@@ -51,9 +55,10 @@ for ns in (18944, 9472, 4736, 2368, 1184, 592, 148, 8):
     z = 5 * (rng.standard_normal(ns) + 1j * rng.standard_normal(ns))
     Q = rng.standard_normal((ns, n)) + 1j * rng.standard_normal((ns, n))
     ref = None
-    for f in ("shallow", "deep"):
+    for f in ("shallow", "deep4", "deep8"):
         for w in (32, 16, 8):
             if ns < 148 and w != 8: continue
+            if f == "shallow" and ns not in (18944, 9472, 8): continue
             flavor(f, w)
             V = g.apply_resolvent(z, Q)
             ms = []
