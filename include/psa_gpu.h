@@ -113,6 +113,17 @@ int psa_gpu_grid(void* ctx, const double* x, int lx, const double* y, int ly, co
                  int maxit, double bigsigma, double* Z, int32_t* iters, int64_t* counts, int* algo,
                  volatile int* cancel);
 
+/* Device-side Schur reordering + truncation: the heavy part of the Trefethen/Wright projection `_maybe_project`
+ * (compute.jl:339-357).  The caller selects the eigenvalues (compute.jl:295-316: cheap host logic on eigA) and passes
+ * their 0-based, ascending positions on the diagonal of the resident square T; the library moves them to the top by
+ * the reference's sequence of Givens swaps -- run as a systolic wavefront on the device instead of one after the other --
+ * truncates to npick x npick and makes that the current matrix of the context (later grid / pseudomode calls use it).
+ * The full matrix stays resident: another psa_gpu_project (a zoom with a different window) starts from it again, and
+ * npick == n restores it.  Tproj: nullable, out, npick x npick column-major interleaved complex (ldp >= npick) -- the
+ * `Tproj` of the reference's return tuple.  Square (:sq_lanc-class) matrices only; multi-device contexts broadcast the
+ * projected matrix over NCCL. */
+int psa_gpu_project(void* ctx, const int32_t* selection, int npick, double* Tproj, int64_t ldp);
+
 /* Row-batched start vectors: the reference draws a NEW random unit q for every batch of rows
  * (`for j=ly:-step:1 ... q = randn(n) + randn(n)*im`, compute.jl:199-208).  q0s holds nbatch vectors of n
  * interleaved complex (vector b at offset b*n); row_batch[j] in [0, nbatch) names the vector used by grid row j

@@ -22,7 +22,7 @@ STAT_NAMES = ("solve_ms", "solve_launches", "total_launches", "grid_ms", "ticks"
               "max_device_ms")
 MATRIX_DEFAULT, MATRIX_UPPER_WRAPPER = 0, 1
 EXPORTS = ("psa_gpu_init", "psa_gpu_set_matrix", "psa_gpu_set_matrix_ex", "psa_gpu_set_matrix_device",
-           "psa_gpu_set_thresholds", "psa_gpu_grid", "psa_gpu_grid_batched", "psa_gpu_grid_device",
+           "psa_gpu_set_thresholds", "psa_gpu_project", "psa_gpu_grid", "psa_gpu_grid_batched", "psa_gpu_grid_device",
            "psa_gpu_postprocess", "psa_gpu_pseudomode", "psa_gpu_apply_resolvent", "psa_gpu_last_stats", "psa_gpu_free",
            "psa_gpu_strerror", "psa_gpu_last_error", "psa_gpu_version")
 
@@ -58,6 +58,7 @@ def load():
     lib.psa_gpu_set_matrix_ex.argtypes = [vp, vp, i64, i32, i32, i32]
     lib.psa_gpu_set_matrix_device.argtypes = [vp, vp, i64, i32, i32]
     lib.psa_gpu_set_thresholds.argtypes = [vp, i32, i32]
+    lib.psa_gpu_project.argtypes = [vp, vp, i32, vp, i64]
     lib.psa_gpu_grid.argtypes = [vp, vp, i32, vp, i32, vp, dbl, i32, dbl, vp, vp, vp, vp, vp]
     lib.psa_gpu_grid_batched.argtypes = [vp, vp, i32, vp, i32, vp, i32, vp, dbl, i32, dbl, vp, vp, vp, vp, vp]
     lib.psa_gpu_postprocess.argtypes = [vp, vp, i32, i32, i32, dbl, dbl, vp, i64, vp, vp]
@@ -148,6 +149,18 @@ class PsaGpu:
         self.shape = None
         self._check(self._lib.psa_gpu_set_matrix_device(self._ctx, dptr, ldt, m, n), "psa_gpu_set_matrix_device")
         self.shape = (m, n)
+
+    def project(self, selection, want_T: bool = True):
+        """Device-side Schur reordering + truncation (compute.jl:339-357): move the eigenvalues at the 0-based ascending
+        diagonal positions `selection` to the top, keep the leading len(selection) x len(selection) block as the
+        current matrix.  Returns Tproj (host copy) or None.  The full matrix stays resident for the next projection."""
+        sel = np.ascontiguousarray(selection, dtype=np.int32)
+        k = len(sel)
+        Tp = np.empty((k, k), dtype=np.complex128, order="F") if want_T else None
+        self._check(self._lib.psa_gpu_project(self._ctx, sel.ctypes.data, k, Tp.ctypes.data if want_T else None, k),
+                    "psa_gpu_project")
+        self.shape = (k, k)
+        return Tp
 
     def grid(self, x, y, q0, tol=1e-5, maxit=99, bigsigma=0.1 * np.finfo(np.float64).max, want_iters=True,
              cancel=None, row_batch=None, want_Z=True):

@@ -91,6 +91,8 @@ def psacore(T, S, q0, x, y, bw, *, tol=1e-5, threaded=False, nt=None, warned=Non
         q0 = np.asarray(q0)[..., :n] @ U.conj()  # rows are start vectors: (U' q)^T = q^T conj(U)
         m = n
     key = _matrix_key(T, thresholds, upper_wrapper)
+    if getattr(ctx, "_matrix_key", None) == key and ctx.shape != (m, n) and m == n and not resident:
+        ctx.project(np.arange(n), want_T=False)  # same matrix, but a projection of it is current: restore the full one
     if not ((resident and ctx.shape == (m, n)) or getattr(ctx, "_matrix_key", None) == key):
         ctx._matrix_key = None
         ctx.set_thresholds(thresholds.minlancs4psa, thresholds.maxstdqr4hess)
@@ -245,13 +247,9 @@ def _givens(f, g):
     return af / d, (f / af) * np.conj(g) / d
 
 
-def _maybe_project(Targ, factor, ax, eigA, thresholds=_default_thresholds, verbosity=0):
-    """Trefethen/Wright projection onto the invariant subspace of the eigenvalues near the window:
-    `_maybe_project(Targ, factor, ax, eigA, thresholds, verbosity) -> (Tproj, eigAproj)`  [src/compute.jl:284-361].
-    A one-time host pre-step (it stays on the host in the reference too); with the default proj_lev = Inf every
-    eigenvalue is selected and T is returned untouched (compute.jl:322-328)."""
-    Targ = np.asarray(Targ)
-    m = Targ.shape[0]
+def _project_selection(m, factor, ax, eigA, thresholds=_default_thresholds):
+    """Which eigenvalues the projection keeps (compute.jl:285-320): 0-based ascending positions, or None when every
+    eigenvalue is selected (no projection)."""
     eigA = np.asarray(eigA)
     axis_w, axis_h = ax[1] - ax[0], ax[3] - ax[2]
     if factor >= 0:
@@ -275,8 +273,33 @@ def _maybe_project(Targ, factor, ax, eigA, thresholds=_default_thresholds, verbo
                 break
     else:
         npick = m
-    if npick == m:
+    return None if npick == m else selection
+
+
+def _maybe_project(Targ, factor, ax, eigA, thresholds=_default_thresholds, verbosity=0, ctx: PsaGpu | None = None):
+    """Trefethen/Wright projection onto the invariant subspace of the eigenvalues near the window:
+    `_maybe_project(Targ, factor, ax, eigA, thresholds, verbosity) -> (Tproj, eigAproj)`  [src/compute.jl:284-361].
+    With the default proj_lev = Inf every eigenvalue is selected and T is returned untouched (compute.jl:322-328).
+    The eigenvalue selection is host logic; the O(np n^2) Givens reordering runs on the device when `ctx` holds Targ
+    (`psa_gpu_project`: the reference's swaps as a systolic wavefront), otherwise on the host exactly like the
+    reference."""
+    Targ = np.asarray(Targ)
+    m = Targ.shape[0]
+    eigA = np.asarray(eigA)
+    if ctx is not None:
+        selection = _project_selection(m, factor, ax, eigA, thresholds)
+        if selection is None:
+            ctx.project(np.arange(m), want_T=False)  # make sure the full matrix is the current one
+            return Targ, eigA.copy()
+        if verbosity > 1:
+            print(f"projection reduces rank {m} -> {len(selection)}")
+        if len(selection) == 0:
+            return np.zeros((0, 0), dtype=np.complex128), eigA[selection]
+        return ctx.project(selection), eigA[selection]
+    selection = _project_selection(m, factor, ax, eigA, thresholds)
+    if selection is None:
         return Targ, eigA.copy()
+    npick = len(selection)
     if verbosity > 1:
         print(f"projection reduces rank {m} -> {npick}")
     eigAproj = eigA[selection]
@@ -386,9 +409,25 @@ def psa_compute(Targ, npts, ax, eigA, opts=None, S=None, *, psatol=1e-5, thresho
     ly = len(y)
     eigAproj = np.array(eigA)
     Tproj = Targ
+    if ctx is None:
+        ctx = _context(ngpus)
+    projected_on_device = False
+    proj_lev = opts.get("proj_lev", math.inf)
     if m == n:  # compute.jl:147-153: projection only for square dense input
-        Tproj, eigAproj = _maybe_project(Targ, opts.get("proj_lev", math.inf), ax, np.asarray(eigA), thresholds,
-                                         opts.get("verbosity", 1))
+        on_device = (math.isfinite(proj_lev) and n >= thresholds.minlancs4psa and opts.get("gpu_project", True)
+                     and _project_selection(m, proj_lev, ax, np.asarray(eigA), thresholds) is not None)
+        if on_device:
+            key = _matrix_key(Targ, thresholds, upper_wrapper)
+            if getattr(ctx, "_matrix_key", None) != key:  # the FULL matrix stays resident across zooms
+                ctx._matrix_key = None
+                ctx.set_thresholds(thresholds.minlancs4psa, thresholds.maxstdqr4hess)
+                ctx.set_matrix(Targ, upper_wrapper=upper_wrapper)
+                ctx._matrix_key = key
+            Tproj, eigAproj = _maybe_project(Targ, proj_lev, ax, np.asarray(eigA), thresholds, opts.get("verbosity", 1),
+                                             ctx=ctx)
+            projected_on_device = True
+        else:
+            Tproj, eigAproj = _maybe_project(Targ, proj_lev, ax, np.asarray(eigA), thresholds, opts.get("verbosity", 1))
         m = Tproj.shape[0]
     nproj = Tproj.shape[1]
     rb, nbatch = row_batches(m, ly)
@@ -405,12 +444,10 @@ def psa_compute(Targ, npts, ax, eigA, opts=None, S=None, *, psatol=1e-5, thresho
         q0 = q0[0]
     # `q = q0[1:n]` (compute.jl:622): after a projection the vector is truncated, NOT renormalised
     q0 = q0[..., :nproj]
-    if ctx is None:
-        ctx = _context(ngpus)
     try:
         _, algo, _ = psacore(Tproj, S, q0, x, y, m - nproj + 1, tol=psatol, thresholds=thresholds, ngpus=ngpus, ctx=ctx,
                              cancel=ctrlflag, row_batch=rb if batched else None, upper_wrapper=upper_wrapper,
-                             keep_on_device=True)
+                             keep_on_device=True, resident=projected_on_device)
     except PsaGpuCancelled:
         return None
     ps_tiny = 10 * math.sqrt(_FLOATMIN)  # compute.jl:236-238

@@ -21,6 +21,7 @@
 #include "psa_hess.cuh"
 #include "psa_nccl.h"
 #include "psa_post.cuh"
+#include "psa_project.cuh"
 #include "psa_square.cuh"
 #include "psa_svd.cuh"
 
@@ -57,7 +58,13 @@ struct Device {
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   // matrix
-  double2* T = nullptr;  // raw copy (m x n, ld = m)
+  double2* T = nullptr;     // raw copy of the matrix as set (m_full x n_full, ld = m_full)
+  double2* Tp = nullptr;    // projected matrix (npick x npick) after psa_gpu_project
+  double2* Tcur = nullptr;  // the matrix the kernels work on: T, or Tp while a projection is active
+  double2* Twork = nullptr; // device 0: scratch copy for the Schur reordering
+  int *proj_sel = nullptr, *proj_start = nullptr;
+  ProjRot* proj_rot = nullptr;
+  size_t Tp_cap = 0, Twork_cap = 0, proj_cap = 0;
   double2* packA = nullptr;
   double2* packB = nullptr;
   size_t T_cap = 0, pack_cap = 0, diag_cap = 0;
@@ -109,7 +116,8 @@ struct Context {
   std::vector<double*> gather_buf; // on device 0: receive buffers for the other devices' tiles
   std::vector<int*> gather_ibuf;
   std::vector<size_t> gather_cap;
-  int m = 0, n = 0, n_pad = 0, nblk = 0, algo = PSA_ALGO_NONE;
+  int m = 0, n = 0, n_pad = 0, nblk = 0, algo = PSA_ALGO_NONE;  // current (possibly projected) matrix
+  int m_full = 0, n_full = 0, algo_full = PSA_ALGO_NONE;         // as set by psa_gpu_set_matrix
   int minlancs = 55, maxstdqr = 200;  // ComputeThresholds, compute.jl:20-27
   double stats[PSA_NSTATS] = {0};
   bool solve_attr_set = false;
@@ -192,7 +200,7 @@ void free_device(Device& d) {
   free_slots(d);
   void* ptrs[] = {d.diagT, d.key_in, d.key_out, d.ord_in, d.ord_out, d.sort_tmp, d.T,     d.packA, d.packB,
                   d.state, d.counts, d.scratch64, d.x,    d.y,       d.Z,        d.q0,    d.row_batch, d.iters,
-                  d.Zfull, d.itfull, d.post,      d.basis, d.yvec};
+                  d.Zfull, d.itfull, d.post,      d.basis, d.yvec, d.Tp, d.Twork, d.proj_sel, d.proj_start, d.proj_rot};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (d.host_state) cudaFreeHost(d.host_state);
@@ -291,6 +299,12 @@ int set_solve_attr(Context* ctx) {
   for (auto& d : ctx->devs) {
     PSA_CUDA(cudaSetDevice(d.dev));
     int rc = solve_set_attrs();
+    if (rc == 0 && cudaFuncSetAttribute(lanczos_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        LZW_WARPS * 2 * LZW_MAX_HIST * (int)sizeof(double)) != cudaSuccess)
+      rc = -1;
+    if (rc == 0 && cudaFuncSetAttribute(lanczos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        2 * HIST_MAX * (int)sizeof(double)) != cudaSuccess)
+      rc = -1;
     if (rc == 0) rc = hess_set_attrs();
     if (rc == 0 && cudaFuncSetAttribute(svd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) rc = -1;
     if (rc != 0) {
@@ -322,7 +336,7 @@ SolveParams solve_params(const Context* ctx, const Device& d) {
   return sp;
 }
 
-// pack / prepare the device-resident matrix on one device (d.T already holds the raw m x n copy)
+// pack / prepare the device-resident matrix on one device (d.Tcur holds the raw ctx->m x ctx->n matrix, ld = ctx->m)
 int prepare_matrix(Context* ctx, Device& d) {
   PSA_CUDA(cudaSetDevice(d.dev));
   if (ctx->algo == PSA_ALGO_SQ_LANC) {
@@ -339,9 +353,9 @@ int prepare_matrix(Context* ctx, Device& d) {
     cudaEventCreate(&e1);
     cudaEventRecord(e0, d.stream);
     if ((rc = ensure_cap(ctx, &d.diagT, &d.diag_cap, (size_t)ctx->n))) return rc;
-    diag_kernel<<<(ctx->n + 255) / 256, 256, 0, d.stream>>>(d.T, ctx->m, ctx->n, d.diagT);
+    diag_kernel<<<(ctx->n + 255) / 256, 256, 0, d.stream>>>(d.Tcur, ctx->m, ctx->n, d.diagT);
     const int grid = (int)std::min<long long>(2 * ntiles, 148LL * 32);
-    pack_kernel<<<grid, 256, 0, d.stream>>>(d.T, ctx->m, ctx->n, ctx->n_pad, ctx->nblk, d.packA, d.packB);
+    pack_kernel<<<grid, 256, 0, d.stream>>>(d.Tcur, ctx->m, ctx->n, ctx->n_pad, ctx->nblk, d.packA, d.packB);
     cudaEventRecord(e1, d.stream);
     PSA_CUDA(cudaGetLastError());
     PSA_CUDA(cudaStreamSynchronize(d.stream));
@@ -465,7 +479,7 @@ int run_grid(Context* ctx, const GridArgs& g, const std::vector<const int*>& row
       SvdParams sp;
       sp.m = ctx->m;
       sp.n = ctx->n;
-      sp.T = d.T;
+      sp.T = d.Tcur;
       sp.P = P[i];
       sp.rows_local = rows[i];
       sp.row0 = i;
@@ -544,7 +558,7 @@ int run_grid(Context* ctx, const GridArgs& g, const std::vector<const int*>& row
       ht.m = ctx->m;
       ht.n = ctx->n;
       ht.n_pad = ctx->n_pad;
-      ht.H = d.T;
+      ht.H = d.Tcur;
       ht.R = d.R;
       ht.q0 = d.q0;
       ht.fresh = d.fresh;
@@ -590,7 +604,7 @@ int run_grid(Context* ctx, const GridArgs& g, const std::vector<const int*>& row
     lp.Z = Zout[i];
     lp.iters = itout[i];
     lp.counts = d.counts;
-    lanczos_kernel<<<bound, LZ_THREADS, 2 * d.hist * sizeof(double), d.stream>>>(lp);
+    launch_lanczos(lp, bound, d.stream);
     launches += 1;
     launch_sched(i, k + 1);
     PSA_CUDA(cudaGetLastError());
@@ -956,7 +970,7 @@ static int set_matrix_common(Context* ctx, const double* T, int64_t ldt, int m, 
   if (!T || m < n || n < 1 || ldt < m) return PSA_ERR_ARG;
   const int algo = classify(ctx, m, n);
   if (algo == PSA_ALGO_NONE) return PSA_ERR_UNSUPPORTED;
-  ctx->algo = PSA_ALGO_NONE;
+  ctx->algo = ctx->algo_full = PSA_ALGO_NONE;
   ctx->last_Z = nullptr;
   // raw copy to device 0
   Device& d0 = ctx->devs[0];
@@ -1003,11 +1017,37 @@ static int set_matrix_common(Context* ctx, const double* T, int64_t ldt, int m, 
     PSA_NCCL(ctx->nccl.GroupEnd());
   }
   ctx->algo = algo;
-  for (auto& d : ctx->devs)
+  ctx->m_full = m;
+  ctx->n_full = n;
+  ctx->algo_full = algo;
+  for (auto& d : ctx->devs) {
+    d.Tcur = d.T;
     if ((rc = prepare_matrix(ctx, d))) {
+      ctx->algo = ctx->algo_full = PSA_ALGO_NONE;
+      return rc;
+    }
+  }
+  return PSA_OK;
+}
+
+// make (m, n, raw pointer) the current matrix on every device and re-pack
+static int activate_matrix(Context* ctx, int m, int n, bool projected) {
+  const int algo = classify(ctx, m, n);
+  if (algo == PSA_ALGO_NONE) return PSA_ERR_UNSUPPORTED;
+  ctx->m = m;
+  ctx->n = n;
+  ctx->n_pad = (n + MB - 1) / MB * MB;
+  ctx->nblk = ctx->n_pad / MB;
+  ctx->algo = algo;
+  ctx->last_Z = nullptr;
+  for (auto& d : ctx->devs) {
+    d.Tcur = projected ? d.Tp : d.T;
+    int rc = prepare_matrix(ctx, d);
+    if (rc) {
       ctx->algo = PSA_ALGO_NONE;
       return rc;
     }
+  }
   return PSA_OK;
 }
 
@@ -1024,6 +1064,72 @@ int psa_gpu_set_matrix_ex(void* vctx, const double* T, int64_t ldt, int m, int n
 int psa_gpu_set_matrix_device(void* vctx, const double* d_T, int64_t ldt, int m, int n) {
   if (!vctx) return PSA_ERR_ARG;
   return set_matrix_common(static_cast<Context*>(vctx), d_T, ldt, m, n, true, PSA_MATRIX_DEFAULT);
+}
+
+int psa_gpu_project(void* vctx, const int32_t* selection, int npick, double* Tproj, int64_t ldp) {
+  if (!vctx) return PSA_ERR_ARG;
+  Context* ctx = static_cast<Context*>(vctx);
+  if (ctx->algo_full == PSA_ALGO_NONE) return PSA_ERR_NOMATRIX;
+  if (ctx->algo_full != PSA_ALGO_SQ_LANC) return PSA_ERR_UNSUPPORTED;  // the reference projects square dense input only
+  const int n = ctx->n_full;
+  if (npick < 1 || npick > n || (npick < n && !selection) || (Tproj && ldp < npick)) return PSA_ERR_ARG;
+  if (npick == n) {  // every eigenvalue selected: the full matrix is (again) the current one (compute.jl:322-328)
+    if (ctx->n == n && ctx->devs[0].Tcur == ctx->devs[0].T) return PSA_OK;
+    return activate_matrix(ctx, ctx->m_full, n, false);
+  }
+  for (int i = 0; i < npick; ++i)
+    if (selection[i] < 0 || selection[i] >= n || (i > 0 && selection[i] <= selection[i - 1])) return PSA_ERR_ARG;
+  if (classify(ctx, npick, npick) == PSA_ALGO_NONE) return PSA_ERR_UNSUPPORTED;
+  Device& d0 = ctx->devs[0];
+  PSA_CUDA(cudaSetDevice(d0.dev));
+  int rc;
+  if ((rc = ensure_cap(ctx, &d0.Twork, &d0.Twork_cap, (size_t)n * n))) return rc;
+  if (d0.proj_cap < (size_t)npick) {
+    d0.proj_cap = 0;
+    if ((rc = dev_alloc(ctx, &d0.proj_sel, (size_t)npick))) return rc;
+    if ((rc = dev_alloc(ctx, &d0.proj_start, (size_t)npick))) return rc;
+    if ((rc = dev_alloc(ctx, &d0.proj_rot, (size_t)npick))) return rc;
+    d0.proj_cap = (size_t)npick;
+  }
+  // wavefront schedule: bubble i starts its swaps at step start[i], two positions behind bubble i-1
+  std::vector<int> start(npick, 0);
+  int steps = 0;
+  for (int i = 0; i < npick; ++i) {
+    if (i > 0) start[i] = start[i - 1] + std::max(0, 2 - (selection[i] - selection[i - 1]));
+    const int len = selection[i] - i;
+    if (len > 0) steps = std::max(steps, start[i] + len);
+  }
+  PSA_CUDA(cudaMemcpyAsync(d0.proj_sel, selection, npick * sizeof(int), cudaMemcpyHostToDevice, d0.stream));
+  PSA_CUDA(cudaMemcpyAsync(d0.proj_start, start.data(), npick * sizeof(int), cudaMemcpyHostToDevice, d0.stream));
+  proj_copy_triu_kernel<<<n, 256, 0, d0.stream>>>(d0.T, ctx->m_full, n, d0.Twork, n);
+  const int gy = std::max(1, std::min(8, (n + 1023) / 1024));
+  for (int t = 0; t < steps; ++t) {
+    proj_params_kernel<<<(npick + 127) / 128, 128, 0, d0.stream>>>(t, npick, d0.proj_sel, d0.proj_start, d0.Twork, n, d0.proj_rot);
+    proj_cols_kernel<<<dim3(npick, gy), 256, 0, d0.stream>>>(npick, d0.proj_rot, d0.Twork, n);
+    proj_rows_kernel<<<dim3(npick, gy), 256, 0, d0.stream>>>(npick, n, d0.proj_rot, d0.Twork, n);
+  }
+  if ((rc = ensure_cap(ctx, &d0.Tp, &d0.Tp_cap, (size_t)npick * npick))) return rc;
+  proj_extract_kernel<<<npick, 256, 0, d0.stream>>>(d0.Twork, n, npick, d0.Tp);
+  PSA_CUDA(cudaGetLastError());
+  if (Tproj)
+    PSA_CUDA(cudaMemcpy2DAsync(Tproj, (size_t)ldp * 16, d0.Tp, (size_t)npick * 16, (size_t)npick * 16, npick,
+                               cudaMemcpyDeviceToHost, d0.stream));
+  PSA_CUDA(cudaStreamSynchronize(d0.stream));
+  if (ctx->devs.size() > 1) {
+    if ((rc = ensure_comms(ctx))) return rc;
+    for (size_t i = 1; i < ctx->devs.size(); ++i) {
+      Device& d = ctx->devs[i];
+      PSA_CUDA(cudaSetDevice(d.dev));
+      if ((rc = ensure_cap(ctx, &d.Tp, &d.Tp_cap, (size_t)npick * npick))) return rc;
+    }
+    PSA_NCCL(ctx->nccl.GroupStart());
+    for (size_t i = 0; i < ctx->devs.size(); ++i) {
+      Device& d = ctx->devs[i];
+      PSA_NCCL(ctx->nccl.Broadcast(d0.Tp, d.Tp, (size_t)npick * npick * 2, ncclDouble, 0, ctx->comms[i], d.stream));
+    }
+    PSA_NCCL(ctx->nccl.GroupEnd());
+  }
+  return activate_matrix(ctx, npick, npick, true);
 }
 
 int psa_gpu_grid(void* vctx, const double* x, int lx, const double* y, int ly, const double* q0, double tol, int maxit,
@@ -1185,7 +1291,7 @@ int psa_gpu_pseudomode(void* vctx, double zre, double zim, const double* q0, dou
     const double2* qcur = it == 1 ? d.q0 : ((it - 1) & 1 ? d.Q1 : d.Q0);
     basis_store_kernel<<<cgrid, 256, 0, d.stream>>>((int)n, qcur, d.basis + (size_t)(it - 1) * n);
     launch_solve(sp, 1, d.num_sms, d.stream);
-    lanczos_kernel<<<1, LZ_THREADS, 2 * d.hist * sizeof(double), d.stream>>>(lp);
+    launch_lanczos(lp, 1, d.stream);
     PSA_CUDA(cudaGetLastError());
     PSA_CUDA(cudaMemcpyAsync(&point, d.slot_point, sizeof(int), cudaMemcpyDeviceToHost, d.stream));
     PSA_CUDA(cudaStreamSynchronize(d.stream));

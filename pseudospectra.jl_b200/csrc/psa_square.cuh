@@ -963,6 +963,164 @@ __global__ void __launch_bounds__(LZ_THREADS) lanczos_kernel(LanczosParams L) {
   }
 }
 
+// Warp-per-slot variant for short vectors (n <= LZW_MAX_N): one warp owns a slot, all reductions are shuffle
+// butterflies (deterministic), no block-level synchronisation, eight slots per CTA.  For the small-matrix configs
+// (README 150 x 150, the 200 x 200 Hessenberg fast path) the CTA-per-slot kernel above spends its time in
+// __syncthreads with one element per thread; this one is ~4x cheaper per tick there.  Which kernel runs depends on
+// n only, never on scheduling, so results stay reproducible.
+constexpr int LZW_MAX_N = 1024;
+constexpr int LZW_WARPS = 8;
+constexpr int LZW_MAX_HIST = 1024;  // 8 warps x 2 x 1024 doubles = 128 KiB of dynamic shared memory at most
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__global__ void __launch_bounds__(LZW_WARPS * 32) lanczos_warp_kernel(LanczosParams L) {
+  extern __shared__ double lz_dyn[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int a = blockIdx.x * LZW_WARPS + wid;
+  if (a >= *L.n_active) return;
+  double* sd = lz_dyn + (size_t)wid * 2 * L.hist;
+  double* se2 = sd + L.hist;
+  const int slot = L.active[a];
+  const int n = L.n;
+  const int sel = L.slot_sel[slot];
+  double2* q = (sel ? L.Q1 : L.Q0) + (size_t)slot * L.n_pad;
+  double2* qold = (sel ? L.Q0 : L.Q1) + (size_t)slot * L.n_pad;
+  double2* w = L.Wv + (size_t)slot * L.n_pad;
+  const int l = L.slot_iter[slot] + 1;
+  const double beta_old = L.slot_beta[slot];
+  const double2* qsrc = (l == 1) ? L.q0 + (size_t)L.slot_batch[slot] * L.n_pad : q;
+
+  double part = 0.0;
+  for (int i = lane; i < n; i += 32) {
+    double2 v = w[i];
+    const double2 qq = qsrc[i];
+    if (l > 1) {
+      const double2 o = qold[i];
+      v.x -= beta_old * o.x;
+      v.y -= beta_old * o.y;
+      w[i] = v;
+    } else {
+      q[i] = qq;
+    }
+    part = fma(qq.x, v.x, part);
+    part = fma(qq.y, v.y, part);
+  }
+  const double alpha = warp_sum(part);
+  part = 0.0;
+  for (int i = lane; i < n; i += 32) {
+    double2 v = w[i];
+    const double2 qq = qsrc[i];
+    v.x -= alpha * qq.x;
+    v.y -= alpha * qq.y;
+    w[i] = v;
+    part = fma(v.x, v.x, part);
+    part = fma(v.y, v.y, part);
+  }
+  const double ss = warp_sum(part);
+  double beta;
+  if (isfinite(ss) && ss > 1e-280) {
+    beta = sqrt(ss);
+  } else {  // scaled 2-norm, as dznrm2
+    double mx = 0.0;
+    for (int i = lane; i < n; i += 32) {
+      const double2 v = w[i];
+      mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+    }
+    mx = warp_max(mx);
+    if (mx == 0.0 || !isfinite(mx)) {
+      beta = mx == 0.0 ? 0.0 : ss;
+    } else {
+      part = 0.0;
+      for (int i = lane; i < n; i += 32) {
+        const double2 v = w[i];
+        const double a_ = v.x / mx, b_ = v.y / mx;
+        part = fma(a_, a_, part);
+        part = fma(b_, b_, part);
+      }
+      beta = mx * sqrt(warp_sum(part));
+    }
+  }
+  for (int i = lane; i < n; i += 32) {
+    const double2 v = w[i];
+    qold[i] = make_double2(v.x / beta, v.y / beta);
+  }
+  double* ha = L.hist_alpha + (size_t)slot * L.hist;
+  double* hb = L.hist_beta + (size_t)slot * L.hist;
+  const bool finite_ab = isfinite(alpha) && isfinite(beta);
+  if (lane == 0) {
+    ha[l - 1] = alpha;
+    hb[l - 1] = beta;
+  }
+  double mx = 0.0;
+  if (finite_ab) {
+    for (int i = lane; i < l; i += 32) {
+      const double a_ = (i == l - 1) ? alpha : ha[i];
+      mx = fmax(mx, fabs(a_));
+      if (i < l - 1) mx = fmax(mx, fabs(hb[i]));
+    }
+  }
+  mx = warp_max(mx);
+  if (finite_ab && mx > 0.0) {
+    for (int i = lane; i < l; i += 32) {
+      const double a_ = (i == l - 1) ? alpha : ha[i];
+      sd[i] = a_ / mx;
+      if (i < l - 1) {
+        const double b_ = hb[i] / mx;
+        se2[i] = b_ * b_;
+      }
+    }
+  }
+  __syncwarp();
+  double sigma;
+  bool failed = false;
+  if (!finite_ab) {
+    sigma = L.bigsigma;
+    failed = true;
+  } else if (mx == 0.0) {
+    sigma = 0.0;
+  } else {
+    sigma = mx * tridiag_max_eig_warp(l, sd, se2, lane);
+  }
+  if (lane == 0) {
+    const double sigold = L.slot_sigold[slot];
+    const bool conv = !failed && (fabs(sigold / sigma - 1.0) < L.tol || beta == 0.0);
+    if (conv || failed || l >= L.maxit) {
+      const int p = L.slot_point[slot];
+      L.Z[p] = 1.0 / sqrt(sigma);
+      if (L.iters) L.iters[p] = l;
+      L.slot_point[slot] = -1;
+      if (!conv) atomicAdd(&L.counts[0], 1ull);
+      if (failed) atomicAdd(&L.counts[1], 1ull);
+      atomicAdd(&L.counts[2], (unsigned long long)l);
+      atomicAdd(&L.counts[3], 1ull);
+    } else {
+      L.slot_sigold[slot] = sigma;
+      L.slot_iter[slot] = l;
+      L.slot_beta[slot] = beta;
+      L.slot_sel[slot] = sel ^ 1;
+    }
+  }
+}
+
+// n_active: upper bound of the device-side count
+inline void launch_lanczos(const LanczosParams& lp, int n_active, cudaStream_t stream) {
+  if (lp.n <= LZW_MAX_N && lp.hist <= LZW_MAX_HIST && !getenv("PSA_LANCZOS_CTA"))
+    lanczos_warp_kernel<<<(n_active + LZW_WARPS - 1) / LZW_WARPS, LZW_WARPS * 32, (size_t)LZW_WARPS * 2 * lp.hist * sizeof(double),
+                          stream>>>(lp);
+  else
+    lanczos_kernel<<<n_active, LZ_THREADS, 2 * lp.hist * sizeof(double), stream>>>(lp);
+}
+
 // ---- helpers for the apply_resolvent diagnostic hook ---------------------------------------------------
 __global__ void load_slots_kernel(int ns, int n, int n_pad, const double2* __restrict__ Q, const double2* __restrict__ z,
                                   double2* __restrict__ Q0, double2* __restrict__ slot_z, int* __restrict__ slot_sel,
@@ -1043,23 +1201,28 @@ inline int solve_flavor() {  // experiments: PSA_SOLVE_FLAVOR=shallow|deep|auto 
   return !strcmp(e, "shallow") ? 0 : !strcmp(e, "deep") ? 1 : 2;
 }
 
-// Panel width for the deep-ring kernel: launch time in units of a full 32-wide round (2 CTAs per SM, 4 consumer
-// warps each), measured on B200 at n = 4000 (profiles/r02_flavor_check_v3.log).  k = 1: at most one CTA per SM, run
-// with 8 consumer warps per CTA (four DMMA-issuing warps per SM sub-partition instead of one: 6.6 ms instead of
-// 8.0 ms for a lone 8-wide panel); k = 2: two CTAs per SM with 4 consumer warps each (register budget).
-inline int pick_deep_width(int n_active, int num_sms) {
+// Panel width for the deep-ring kernel.  A launch costs (GEMM steps) x tg + (diagonal steps) x td per panel round, with
+// per-step times (clock cycles per CTA, wall clock) measured on B200 at n = 4000 (profiles/r02_flavor_check_v3.log,
+// r02_phase_timing_deep_v2.log) for k = 1 (at most one CTA per SM: run with 8 consumer warps, four DMMA-issuing warps per
+// SM sub-partition) and k = 2 (two CTAs per SM, 4 consumer warps each: register budget).  The diagonal steps cost
+// about the same for every width, so small matrices (few block rows: diagonal-dominated) prefer wide panels and
+// large ones prefer whatever fills the SMs evenly.
+inline int pick_deep_width(int n_active, int num_sms, int nblk) {
   const char* env = getenv("PSA_PANEL_WIDTH");  // experiments only
   const int forced = env ? atoi(env) : 0;
   if (forced == 32 || forced == 16 || forced == 8) return forced;
   static const int widths[3] = {8, 16, 32};
-  static const double cost[3][3] = {{0.0, 0.186, 0.299}, {0.0, 0.304, 0.536}, {0.0, 0.553, 1.000}};
+  static const double tg[3][3] = {{0, 739, 1195}, {0, 1240, 2236}, {0, 2340, 4300}};
+  static const double td[3][3] = {{0, 3300, 5000}, {0, 4300, 6000}, {0, 5300, 7000}};
+  const double G = 2.0 * nblk * (nblk - 1), D = 4.0 * nblk;
   int best = 32;
   double best_cost = 1e300;
   for (int i = 0; i < 3; ++i) {
     const int panels = (n_active + widths[i] - 1) / widths[i];
     const int rounds = panels / (2 * num_sms), rest = panels % (2 * num_sms);
-    const double c = rounds * cost[i][2] + (rest == 0 ? 0.0 : cost[i][rest <= num_sms ? 1 : 2]);
-    if (c < best_cost - 1e-12) {
+    const double t1 = G * tg[i][1] + D * td[i][1], t2 = G * tg[i][2] + D * td[i][2];
+    const double c = rounds * t2 + (rest == 0 ? 0.0 : (rest <= num_sms ? t1 : t2));
+    if (c < best_cost * (1.0 - 1e-9)) {
       best_cost = c;
       best = widths[i];
     }
@@ -1080,7 +1243,7 @@ inline void launch_deep(const SolveParams& sp, int width, int panels, cudaStream
 // default; PSA_SOLVE_FLAVOR=shallow selects the round-1 choreography (same results bit for bit) for A/B timing.
 inline void launch_solve(const SolveParams& sp, int n_active, int num_sms, cudaStream_t stream) {
   if (solve_flavor() != 0) {
-    const int width = pick_deep_width(n_active, num_sms);
+    const int width = pick_deep_width(n_active, num_sms, sp.nblk);
     const int panels = (n_active + width - 1) / width;
     const char* ecw = getenv("PSA_DEEP_CW");  // experiments only
     const int cw = ecw ? atoi(ecw) : (panels <= num_sms ? 8 : 4);

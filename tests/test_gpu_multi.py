@@ -70,3 +70,18 @@ def test_multi_device_batched_q_and_device_postprocess(pkg):
         assert np.array_equal(np.asarray(a), np.asarray(b))
     Zo, yo = po.unmirror(res[0][0], y, nm)
     assert np.array_equal(res[0][3], np.clip(Zo, po.PS_TINY, np.inf)) and np.array_equal(res[0][4], yo)
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+def test_multi_device_projection(pkg):
+    """psa_gpu_project on a multi-device context: reordered on device 0, the projected matrix broadcast over NCCL."""
+    T, eigA = po.complex_schur(po.random_complex(260, 8))
+    ax = [-5.0, 5.0, -5.0, 5.0]
+    q0 = po.start_vector(260, 0)
+    res = []
+    for ng in (1, 2):
+        with pkg.PsaGpu(ng) as g:
+            out = pkg.psa_compute(T, 9, ax, eigA, {"proj_lev": 0.6}, q0=q0, ctx=g)
+            res.append(out)
+    assert res[0][5].shape == res[1][5].shape and 55 <= res[0][5].shape[0] < 260
+    assert np.array_equal(res[0][5], res[1][5]) and np.array_equal(res[0][0], res[1][0])

@@ -630,3 +630,55 @@ def test_hessqr_shared_schur_fast_path(pkg, gpu):
     Zf, algo_f, _, itf = pkg.psacore(H, None, q0, x, y, 2, ctx=gpu, want_iters=True, hess_via_schur=True)
     assert algo_g == algo_f == "HessQR"
     assert _rel(Zf, Zg, _floor(H)) < RTOL and np.mean(itf == itg) >= 0.97
+
+
+def test_device_projection_matches_host_restatement(pkg, gpu):
+    """psa_gpu_project (the Givens reordering of _maybe_project, compute.jl:339-357, as a device wavefront) against the
+    host restatement of the reference's sequential swaps: same projected matrix to rounding, same eigenvalue order,
+    and the grid on it agrees with the oracle's Lanczos on the host-projected matrix."""
+    from pseudospectra_jl_b200 import compute as hc
+    T, eigA = po.complex_schur(po.random_complex(300, 6))
+    ax = [-5.0, 5.0, -5.0, 5.0]
+    q0 = po.start_vector(300, 0)
+    Th, eh = hc._maybe_project(T, 0.6, ax, eigA)                      # host: sequential swaps, as the reference
+    gpu._matrix_key = None
+    out = pkg.psa_compute(T, 14, ax, eigA, {"proj_lev": 0.6}, q0=q0, ctx=gpu)
+    Z, x, y, levels, err, Tp, ep, algo = out
+    k = Th.shape[0]
+    assert 55 <= k < 300 and Tp.shape == (k, k) and algo == "sq_lanc" and np.array_equal(ep, eh)
+    assert np.abs(np.tril(Tp, -1)).max() == 0
+    assert np.allclose(np.diagonal(Tp), eh, rtol=0, atol=1e-11 * np.abs(eigA).max())
+    assert np.linalg.norm(Tp - Th) <= 1e-11 * np.linalg.norm(Th)
+    Zc, _, _ = co.grid(Th, x, y, q0[:k], nthreads=os.cpu_count() or 8)
+    assert _rel(Z, np.clip(Zc, po.PS_TINY, np.inf), _floor(Th)) < RTOL
+    # zoom with another window: projected again from the resident FULL matrix, no upload
+    calls = []
+    orig = gpu.set_matrix
+    gpu.set_matrix = lambda *a, **kw: (calls.append(1), orig(*a, **kw))[1]
+    try:
+        ax2 = [-2.0, 3.0, -1.0, 4.0]
+        out2 = pkg.psa_compute(T, 10, ax2, eigA, {"proj_lev": 0.4}, q0=q0, ctx=gpu)
+        Th2, eh2 = hc._maybe_project(T, 0.4, ax2, eigA)
+        assert calls == [] and out2[5].shape == Th2.shape and np.array_equal(out2[6], eh2)
+        if Th2.shape[0] >= 55:
+            Zc2, _, _ = co.grid(Th2, out2[1], out2[2], q0[:Th2.shape[0]], nthreads=os.cpu_count() or 8)
+            assert _rel(out2[0], np.clip(Zc2, po.PS_TINY, np.inf), _floor(Th2)) < RTOL
+        out3 = pkg.psa_compute(T, 6, ax, eigA, {}, q0=q0, ctx=gpu)   # no projection: the full matrix is current again
+        assert calls == [] and out3[5] is T and gpu.shape == (300, 300)
+        Zc3, _, _ = co.grid(T, out3[1], out3[2], q0, nthreads=os.cpu_count() or 8)
+        assert _rel(out3[0], np.clip(Zc3, po.PS_TINY, np.inf), _floor(T)) < RTOL
+    finally:
+        gpu.set_matrix = orig
+
+
+def test_projection_below_minlancs_uses_svd_branch(pkg, gpu):
+    """A projection can shrink T below minlancs4psa (minnev = 20 <= np): the reference then takes the SVD branch on the
+    projected matrix; so does the device path."""
+    T, eigA = po.complex_schur(po.random_complex(120, 6))
+    ax = [-3.0, 3.0, -3.0, 3.0]
+    gpu._matrix_key = None
+    out = pkg.psa_compute(T, 8, ax, eigA, {"proj_lev": 0.5}, q0=po.start_vector(120, 0), ctx=gpu)
+    k = out[5].shape[0]
+    assert 20 <= k < 55 and out[7] == "SVD"
+    svd = np.array([[po.sigmin_svd(out[5], xx + 1j * yy) for xx in out[1]] for yy in out[2]])
+    assert np.max(np.abs(out[0] - svd) / svd) < 1e-9

@@ -16,7 +16,7 @@ class _FakeCtx:
         self.calls.append(("thr", a, b))
 
     def set_matrix(self, T, upper_wrapper=False):
-        self.T = np.array(T)
+        self.T = self.Tfull = np.array(T)
         self.shape = T.shape
         self.calls.append(("set", T.shape))
 
@@ -31,6 +31,34 @@ class _FakeCtx:
         self.calls.append(("grid", len(x), len(y)))
         algo = "sq_lanc" if self.T.shape[0] == self.T.shape[1] else "HessQR"
         return (Z if want_Z else None), None, np.zeros(4, dtype=np.int64), algo
+
+    def project(self, selection, want_T=True):
+        from pseudospectra_jl_b200 import compute as hc
+        self.calls.append(("project", len(selection)))
+        if len(selection) == self.Tfull.shape[0]:
+            self.T, self.shape = self.Tfull, self.Tfull.shape
+            return None
+        eig = np.diagonal(self.Tfull)
+        class Th:  # selects exactly `selection`
+            minnev = 0
+        Tp = self.Tfull
+        # reuse the host restatement of the swaps
+        sel = np.asarray(selection)
+        Tp = np.triu(np.array(self.Tfull, dtype=np.complex128))
+        for i in range(len(sel)):
+            for k in range(sel[i] - 1, i - 1, -1):
+                c, sn = hc._givens(np.conj(Tp[k, k + 1]), np.conj(Tp[k, k] - Tp[k + 1, k + 1]))
+                sn = -np.conj(sn)
+                a1, a2 = Tp[:, k].copy(), Tp[:, k + 1].copy()
+                Tp[:, k] = a1 * c + a2 * np.conj(sn)
+                Tp[:, k + 1] = -a1 * sn + a2 * c
+                r1, r2 = Tp[k, :].copy(), Tp[k + 1, :].copy()
+                Tp[k, :] = c * r1 + sn * r2
+                Tp[k + 1, :] = -np.conj(sn) * r1 + c * r2
+        k = len(sel)
+        self.T = np.asfortranarray(np.triu(Tp[:k, :k]))
+        self.shape = (k, k)
+        return self.T if want_T else None
 
     def postprocess(self, y, lx, n_mirror, ps_tiny, small_sigma=1e-150):
         Z, yf = po.unmirror(self._Z, np.asarray(y), n_mirror)
@@ -65,3 +93,23 @@ def test_psacore_hess_fast_path_plumbing(pkg):
     assert algo_g == algo_f == "HessQR" and c2.shape == (229, 229) and c1.shape == (230, 229)
     ok = Zg > 1e-9
     assert np.allclose(Zf[ok], Zg[ok], rtol=1e-6)
+
+
+def test_psa_compute_device_projection_plumbing(pkg):
+    """proj_lev finite: the full matrix is uploaded once, projected on the `device`, the grid runs on the projected
+    matrix with the TRUNCATED (not renormalised) start vector; a second call without projection restores the full one."""
+    T, eigA = po.complex_schur(po.random_complex(200, 6))
+    ax = [-4.0, 4.0, -4.0, 4.0]
+    q0 = po.start_vector(200, 0)
+    ctx = _FakeCtx()
+    out = pkg.psa_compute(T, 6, ax, eigA, {"proj_lev": 1.0}, q0=q0, ctx=ctx)
+    from pseudospectra_jl_b200 import compute as hc
+    Tp, ep = hc._maybe_project(T, 1.0, ax, eigA)
+    k = Tp.shape[0]
+    assert 55 <= k < 200 and out[5].shape == (k, k) and np.allclose(out[5], Tp) and np.array_equal(out[6], ep)
+    import c_oracle as co
+    Zc = np.clip(co.grid(Tp, out[1], out[2], q0[:k])[0], po.PS_TINY, np.inf)
+    assert np.allclose(out[0], Zc, rtol=1e-9)
+    assert [c[0] for c in ctx.calls].count("set") == 1
+    out2 = pkg.psa_compute(T, 5, ax, eigA, {}, q0=q0, ctx=ctx)   # no projection: full matrix again, no re-upload
+    assert [c[0] for c in ctx.calls].count("set") == 1 and ctx.shape == (200, 200) and out2[5] is T
