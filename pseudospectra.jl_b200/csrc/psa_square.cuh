@@ -408,19 +408,25 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 4) solve_kernel(SolveParams P) 
 // sub-partition at 2 CTAs per SM) + 1 producer warp.
 __host__ __device__ constexpr int deep_threads(int cw) { return cw * 32 + 32; }
 
+// X tile rows are 256 B (16 complex), UNPADDED, with a one-bit swizzle instead: the 16-byte element e of row s sits at
+// position e ^ (4 * (s & 1)).  A quarter-warp of a B-fragment LDS.128 covers rows (s, s+1) x four consecutive elements:
+// the two rows then use complementary halves of the 32 banks -- conflict-free like the 320-byte padded rows of
+// solve_kernel, with 8 % smaller stages (deeper rings in the same shared memory).
+constexpr int XROW_D = KC * 16;
+__host__ __device__ constexpr int deep_stage_bytes(int nsv) { return TILE_BYTES + nsv * XROW_D; }
 template <int NSV, int S>
-__host__ __device__ constexpr int deep_smem() { return S * stage_bytes(NSV) + 128 + NSV * 16 + NSV * 8 * 2; }
+__host__ __device__ constexpr int deep_smem() { return S * deep_stage_bytes(NSV) + 128 + NSV * 16 + NSV * 8 * 2; }
 
 template <int THREADS>
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 
 template <int NSV, int S, int CW>
-__global__ void __launch_bounds__(deep_threads(CW), 2) solve_deep_kernel(SolveParams P) {
+__device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
   static_assert(S >= 3 && S <= 8 && (CW == 4 || CW == 8), "ring geometry");
   constexpr int NT = NSV / 8;
   constexpr int MT = 8 / CW;              // 8-row DMMA tiles per consumer warp
   constexpr int CTHREADS = CW * 32;       // consumer threads
-  constexpr int STAGE_BYTES = stage_bytes(NSV);
+  constexpr int STAGE_BYTES = deep_stage_bytes(NSV);
   extern __shared__ __align__(128) unsigned char smem[];
   const int n_active = *P.n_active;
   const int panel = blockIdx.x;
@@ -488,7 +494,7 @@ __global__ void __launch_bounds__(deep_threads(CW), 2) solve_deep_kernel(SolvePa
       for (int seg = lane; seg < NSV * KC; seg += 32) {  // 16-byte segments: row = seg / KC
         const int s = seg / KC, part = seg % KC;
         const double2* src = (from_q ? qptr[s] : (const double2*)wptr[s]) + mem0 + part;
-        cp_async16_hint(sb + TILE_BYTES + s * XROW_BYTES + part * 16, src, pol_X);
+        cp_async16_hint(sb + TILE_BYTES + s * XROW_D + ((part ^ ((s & 1) << 2)) << 4), src, pol_X);
       }
       cp_async_mbar_arrive_noinc(&full_bar[stage]);
       pc.advance();
@@ -506,7 +512,8 @@ __global__ void __launch_bounds__(deep_threads(CW), 2) solve_deep_kernel(SolvePa
 
   auto gemm_step = [&](const unsigned char* sb, int flip) {
     const double2* At = reinterpret_cast<const double2*>(sb);
-    const unsigned char* Xt = sb + TILE_BYTES + (lane >> 2) * XROW_BYTES;
+    const unsigned char* Xt = sb + TILE_BYTES + (lane >> 2) * XROW_D;
+    const int fx = flip ^ (((lane >> 2) & 1) << 2);  // memory-order flip of the plain solve + the row swizzle
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       double2 a[MT], b[NT];
@@ -514,7 +521,7 @@ __global__ void __launch_bounds__(deep_threads(CW), 2) solve_deep_kernel(SolvePa
       for (int mt = 0; mt < MT; ++mt) a[mt] = At[(j * 8 + MT * wm + mt) * 32 + lane];
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt)
-        b[nt] = *reinterpret_cast<const double2*>(Xt + nt * 8 * XROW_BYTES + (((4 * j + (lane & 3)) ^ flip) << 4));
+        b[nt] = *reinterpret_cast<const double2*>(Xt + nt * 8 * XROW_D + (((4 * j + (lane & 3)) ^ fx) << 4));
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -565,7 +572,7 @@ __global__ void __launch_bounds__(deep_threads(CW), 2) solve_deep_kernel(SolvePa
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int r = 8 * ((MT * wm + mt) & 1) + (lane >> 2), sl = 8 * nt + 2 * (lane & 3) + e;
-              double2* pb = reinterpret_cast<double2*>(Xt + sl * XROW_BYTES + ((r ^ flip) << 4));
+              double2* pb = reinterpret_cast<double2*>(Xt + sl * XROW_D + ((r ^ flip ^ (e << 2)) << 4));  // sl & 1 == e
               const double2 g = *pb;
               *pb = make_double2(g.x - cre[mt][nt][e], g.y - cim[mt][nt][e]);
               cre[mt][nt][e] = 0.0;
@@ -580,7 +587,8 @@ __global__ void __launch_bounds__(deep_threads(CW), 2) solve_deep_kernel(SolvePa
         const int s = solver ? grp : 0;
         static_assert(NSV <= GROUPS, "one 4-lane group per shift");
         const int mem0 = cons.phase ? n_pad - KC * cons.c - KC : KC * cons.c;
-        double2* xrow = reinterpret_cast<double2*>(Xt + s * XROW_BYTES);
+        double2* xrow = reinterpret_cast<double2*>(Xt + s * XROW_D);
+        const int fs = flip ^ ((s & 1) << 2);  // flip + row swizzle of this shift's row
         const double2* At = reinterpret_cast<const double2*>(sb);
         double2 zt = zsh[s];
         if (cons.phase == 0) zt.y = -zt.y;  // adjoint system: diagonal conj(t_ii - z)
@@ -589,7 +597,7 @@ __global__ void __launch_bounds__(deep_threads(CW), 2) solve_deep_kernel(SolvePa
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = 4 * i + pl, m = KC * cp + r;
-          b[i] = xrow[r ^ flip];
+          b[i] = xrow[r ^ fs];
           double2 d = At[((r >> 2) * 8 + (m >> 3)) * 32 + (m & 7) * 4 + (r & 3)];
           d.x -= zt.x;
           d.y -= zt.y;
@@ -621,7 +629,7 @@ __global__ void __launch_bounds__(deep_threads(CW), 2) solve_deep_kernel(SolvePa
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int r = 4 * i + pl;
-            xrow[r ^ flip] = b[i];
+            xrow[r ^ fs] = b[i];
             op_[r ^ flip] = b[i];
           }
         }
@@ -642,6 +650,12 @@ __global__ void __launch_bounds__(deep_threads(CW), 2) solve_deep_kernel(SolvePa
     printf("[timing deep] cta %d warp %d: load-wait %lld gemm %lld diag %lld release %lld clk, %d steps\n", (int)blockIdx.x,
            warp, tm_wait, tm_gemm, tm_diag, tm_sync, total_steps);
 #endif
+}
+
+// one CTA (sparse launches) or two CTAs per SM: the register file is not the limit
+template <int NSV, int S, int CW, int OCC>
+__global__ void __launch_bounds__(deep_threads(CW), OCC) solve_deep_kernel(SolveParams P) {
+  solve_deep_body<NSV, S, CW>(P);
 }
 
 // ---- scheduler: refill idle slots from the point queue, compact the active list -------------------------
@@ -1174,8 +1188,15 @@ inline int pick_panel_width(int n_active, int num_sms) {
   return best;
 }
 
-// ring geometry of the deep variant per panel width (shared memory for 2 CTAs per SM)
-constexpr int DEEP_S32 = 4, DEEP_S16 = 5, DEEP_S8 = 6;
+// Instantiations of the deep-ring kernel.  "Full" launches (more panels than SMs): 2 CTAs per SM, 4 consumer warps
+// each, the deepest ring that fits twice into shared memory.  (Measured and not adopted, profiles/r02_flavor_check_v4.log:
+// 3 CTAs per SM with 3-stage rings and 136 registers -- 30.7 TFLOP/s against 33.6: ring depth matters more than a third
+// DMMA-issuing warp per sub-partition; 8 consumer warps at 2 CTAs per SM -- 96 registers, spills, 32.4 TFLOP/s.)
+// "Sparse" launches (at most one panel per SM: grid tails, strong scaling over many GPUs, the pseudomode): one CTA per
+// SM with 8 consumer warps (four DMMA-issuing warps per sub-partition) and 6..8 stages.
+constexpr int DEEP_OCC = 2;
+constexpr int DEEP_S32 = 4, DEEP_S16 = 5, DEEP_S8 = 6;        // 2 CTAs per SM, CW = 4
+constexpr int SPARSE_S32 = 6, SPARSE_S16 = 8, SPARSE_S8 = 8;  // one CTA per SM, CW = 8
 
 inline int solve_set_attrs() {
   cudaError_t e = cudaSuccess;
@@ -1186,12 +1207,12 @@ inline int solve_set_attrs() {
   set(solve_kernel<32>, solve_smem(32));
   set(solve_kernel<16>, solve_smem(16));
   set(solve_kernel<8>, solve_smem(8));
-  set(solve_deep_kernel<32, DEEP_S32, 4>, deep_smem<32, DEEP_S32>());
-  set(solve_deep_kernel<32, DEEP_S32, 8>, deep_smem<32, DEEP_S32>());
-  set(solve_deep_kernel<16, DEEP_S16, 4>, deep_smem<16, DEEP_S16>());
-  set(solve_deep_kernel<16, DEEP_S16, 8>, deep_smem<16, DEEP_S16>());
-  set(solve_deep_kernel<8, DEEP_S8, 4>, deep_smem<8, DEEP_S8>());
-  set(solve_deep_kernel<8, DEEP_S8, 8>, deep_smem<8, DEEP_S8>());
+  set(solve_deep_kernel<32, DEEP_S32, 4, DEEP_OCC>, deep_smem<32, DEEP_S32>());
+  set(solve_deep_kernel<16, DEEP_S16, 4, DEEP_OCC>, deep_smem<16, DEEP_S16>());
+  set(solve_deep_kernel<8, DEEP_S8, 4, DEEP_OCC>, deep_smem<8, DEEP_S8>());
+  set(solve_deep_kernel<32, SPARSE_S32, 8, 1>, deep_smem<32, SPARSE_S32>());
+  set(solve_deep_kernel<16, SPARSE_S16, 8, 1>, deep_smem<16, SPARSE_S16>());
+  set(solve_deep_kernel<8, SPARSE_S8, 8, 1>, deep_smem<8, SPARSE_S8>());
   return e == cudaSuccess ? 0 : -1;
 }
 
@@ -1202,7 +1223,7 @@ inline int solve_flavor() {  // experiments: PSA_SOLVE_FLAVOR=shallow|deep|auto 
 }
 
 // Panel width for the deep-ring kernel.  A launch costs (GEMM steps) x tg + (diagonal steps) x td per panel round, with
-// per-step times (clock cycles per CTA, wall clock) measured on B200 at n = 4000 (profiles/r02_flavor_check_v3.log,
+// per-step times (clock cycles per CTA, wall clock) measured on B200 at n = 4000 (profiles/r02_flavor_check_v3.log, r02_flavor_check_v4.log,
 // r02_phase_timing_deep_v2.log) for k = 1 (at most one CTA per SM: run with 8 consumer warps, four DMMA-issuing warps per
 // SM sub-partition) and k = 2 (two CTAs per SM, 4 consumer warps each: register budget).  The diagonal steps cost
 // about the same for every width, so small matrices (few block rows: diagonal-dominated) prefer wide panels and
@@ -1212,8 +1233,8 @@ inline int pick_deep_width(int n_active, int num_sms, int nblk) {
   const int forced = env ? atoi(env) : 0;
   if (forced == 32 || forced == 16 || forced == 8) return forced;
   static const int widths[3] = {8, 16, 32};
-  static const double tg[3][3] = {{0, 739, 1195}, {0, 1240, 2236}, {0, 2340, 4300}};
-  static const double td[3][3] = {{0, 3300, 5000}, {0, 4300, 6000}, {0, 5300, 7000}};
+  static const double tg[3][3] = {{0, 679, 1195}, {0, 1190, 2236}, {0, 2235, 4300}};
+  static const double td[3][3] = {{0, 3000, 5000}, {0, 3800, 6000}, {0, 4800, 7000}};
   const double G = 2.0 * nblk * (nblk - 1), D = 4.0 * nblk;
   int best = 32;
   double best_cost = 1e300;
@@ -1230,12 +1251,19 @@ inline int pick_deep_width(int n_active, int num_sms, int nblk) {
   return best;
 }
 
-template <int CW>
-inline void launch_deep(const SolveParams& sp, int width, int panels, cudaStream_t stream) {
+inline void launch_deep(const SolveParams& sp, int width, int panels, bool sparse, cudaStream_t stream) {
+  if (sparse) {
+    switch (width) {
+      case 32: solve_deep_kernel<32, SPARSE_S32, 8, 1><<<panels, deep_threads(8), deep_smem<32, SPARSE_S32>(), stream>>>(sp); break;
+      case 16: solve_deep_kernel<16, SPARSE_S16, 8, 1><<<panels, deep_threads(8), deep_smem<16, SPARSE_S16>(), stream>>>(sp); break;
+      default: solve_deep_kernel<8, SPARSE_S8, 8, 1><<<panels, deep_threads(8), deep_smem<8, SPARSE_S8>(), stream>>>(sp); break;
+    }
+    return;
+  }
   switch (width) {
-    case 32: solve_deep_kernel<32, DEEP_S32, CW><<<panels, deep_threads(CW), deep_smem<32, DEEP_S32>(), stream>>>(sp); break;
-    case 16: solve_deep_kernel<16, DEEP_S16, CW><<<panels, deep_threads(CW), deep_smem<16, DEEP_S16>(), stream>>>(sp); break;
-    default: solve_deep_kernel<8, DEEP_S8, CW><<<panels, deep_threads(CW), deep_smem<8, DEEP_S8>(), stream>>>(sp); break;
+    case 32: solve_deep_kernel<32, DEEP_S32, 4, DEEP_OCC><<<panels, deep_threads(4), deep_smem<32, DEEP_S32>(), stream>>>(sp); break;
+    case 16: solve_deep_kernel<16, DEEP_S16, 4, DEEP_OCC><<<panels, deep_threads(4), deep_smem<16, DEEP_S16>(), stream>>>(sp); break;
+    default: solve_deep_kernel<8, DEEP_S8, 4, DEEP_OCC><<<panels, deep_threads(4), deep_smem<8, DEEP_S8>(), stream>>>(sp); break;
   }
 }
 
@@ -1245,10 +1273,9 @@ inline void launch_solve(const SolveParams& sp, int n_active, int num_sms, cudaS
   if (solve_flavor() != 0) {
     const int width = pick_deep_width(n_active, num_sms, sp.nblk);
     const int panels = (n_active + width - 1) / width;
-    const char* ecw = getenv("PSA_DEEP_CW");  // experiments only
-    const int cw = ecw ? atoi(ecw) : (panels <= num_sms ? 8 : 4);
-    if (cw == 4) launch_deep<4>(sp, width, panels, stream);
-    else launch_deep<8>(sp, width, panels, stream);
+    const char* ecw = getenv("PSA_DEEP_CW");  // experiments only: 8 = sparse instantiation, 4 = full one
+    const bool sparse = ecw ? atoi(ecw) == 8 : panels <= num_sms;
+    launch_deep(sp, width, panels, sparse, stream);
     return;
   }
   const int width = pick_panel_width(n_active, num_sms);
