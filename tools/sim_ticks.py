@@ -1,33 +1,40 @@
 """Scheduler model used for the scaling analysis in DESIGN.md: replays the tick loop on the measured per-point
-Lanczos iteration counts of the bench workload (profiles/r01_iters_n4000.npz) with the measured launch times of
-profiles/r01_panel_sweep.txt, for 1/2/4/8 row-cyclic shards.  CPU only.
+Lanczos iteration counts of the bench workload (profiles/r01_iters_n4000.npz) with the measured launch times of the
+round-2 solve kernels (profiles/r02_flavor_check_v3.log / _v4.log), for 1/2/4/8 row-cyclic shards.  CPU only.
 
-    python tools/sim_ticks.py
+    python tools/sim_ticks.py [sparse_ms_w8]      # optional: what-if lone-panel latency of the 8-wide sparse launch
 """
 import os
+import sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 it = np.load(os.path.join(ROOT, "profiles", "r01_iters_n4000.npz"))["iters"].astype(int)
 SMS, W = 148, 18944
-# ms per launch with k = 1..4 co-resident CTAs per SM, by panel width (n = 4000)
-COST = {8: [0, 9.7, 11.98, 16.5, 20.65], 16: [0, 15.3, 21.45, 30.0, 38.3], 32: [0, 25.8, 37.6, 57.0, 73.85]}
-FULL_RATE = W / COST[32][4]  # shift-iterations per ms at full occupancy
+# ms per launch at n = 4000 by panel width: [sparse: <= 1 panel per SM (8 consumer warps), full round: 2 CTAs per SM]
+COST = {8: [6.17, 10.78], 16: [10.44, 19.32], 32: [19.0, 36.06]}
+if len(sys.argv) > 1:
+    s = float(sys.argv[1]) / COST[8][0]
+    for w in COST:
+        COST[w][0] *= s
+FULL_RATE = 2 * SMS * 32 / COST[32][1]  # shift-iterations per ms at full occupancy
 
 
 def tick_ms(n):
     best = 1e9
-    for w, c in COST.items():
-        per_sm = -(-(-(-n // w)) // SMS)
-        best = min(best, (per_sm // 4) * c[4] + c[per_sm % 4])
+    for w, (c1, c2) in COST.items():
+        panels = -(-n // w)
+        rounds, rest = divmod(panels, 2 * SMS)
+        best = min(best, rounds * c2 + (0 if rest == 0 else (c1 if rest <= SMS else c2)))
     return best
 
 
-def simulate(iters):
-    iters = np.sort(iters)[::-1]  # longest-job-first queue (ideal predictor)
+def simulate(iters, order="ljf"):
+    iters = np.sort(iters)[::-1] if order == "ljf" else iters  # longest-job-first queue (ideal predictor)
+    cap = W if len(iters) >= W or len(iters) <= W // 2 else W // 2
     head, rem, t, ticks = 0, np.zeros(0, int), 0.0, 0
     while head < len(iters) or len(rem):
-        take = min(W - len(rem), len(iters) - head)
+        take = min(cap - len(rem), len(iters) - head)
         if take > 0:
             rem = np.concatenate([rem, iters[head:head + take]])
             head += take
