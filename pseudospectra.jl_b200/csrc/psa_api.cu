@@ -23,6 +23,7 @@
 #include "psa_post.cuh"
 #include "psa_project.cuh"
 #include "psa_square.cuh"
+#include "psa_cluster.cuh"
 #include "psa_svd.cuh"
 
 namespace {
@@ -274,13 +275,14 @@ int slot_capacity(const Context* ctx, const Device& d, long long points) {
   if (is_hess_algo(ctx->algo)) {
     cap = hess_slot_capacity(ctx->n, d.num_sms);
   } else {
-    cap = 4LL * d.num_sms * NS;  // two rounds of two resident solve CTAs per SM, NS shifts each
+    // exactly ONE round of resident solve CTAs (2 per SM, NS shifts each): with more slots than that every tick whose
+    // active count is not a multiple of a round pays for a partially filled extra round.  Replaying the tick loop on
+    // the measured iteration counts of the bench workload (tools/sim_ticks.py) gives 0.87 strong-scaling efficiency at
+    // 8 GPUs with two rounds of slots and 0.97 with one; a single GPU is unaffected (twice the ticks, half as long).
+    cap = 2LL * d.num_sms * NS;
+    if (solve_flavor() == 0) cap = 4LL * d.num_sms * NS;  // the round-1 kernel keeps 4 CTAs per SM resident
   }
   long long w = std::min(cap, (points + NS - 1) / NS * NS);
-  // between one and two full rounds of panels, every tick would pay for a second, nearly empty round: keep exactly
-  // one round of slots in flight and let the remaining points wait in the queue
-  const long long round = 2LL * d.num_sms * NS;
-  if (!is_hess_algo(ctx->algo) && w > round && w < 2 * round) w = round;
   return (int)std::max<long long>(w, NS);
 }
 
@@ -299,6 +301,7 @@ int set_solve_attr(Context* ctx) {
   for (auto& d : ctx->devs) {
     PSA_CUDA(cudaSetDevice(d.dev));
     int rc = solve_set_attrs();
+    if (rc == 0) rc = cluster_set_attrs();
     if (rc == 0 && cudaFuncSetAttribute(lanczos_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         LZW_WARPS * 2 * LZW_MAX_HIST * (int)sizeof(double)) != cudaSuccess)
       rc = -1;
@@ -550,7 +553,7 @@ int run_grid(Context* ctx, const GridArgs& g, const std::vector<const int*>& row
     EventPair& ep = event_pair(d, t.nev++);
     if (ctx->algo == PSA_ALGO_SQ_LANC) {
       PSA_CUDA(cudaEventRecord(ep.a, d.stream));
-      launch_solve(solve_params(ctx, d), bound, d.num_sms, d.stream);
+      launch_solve_auto(solve_params(ctx, d), bound, d.num_sms, d.stream);
       PSA_CUDA(cudaEventRecord(ep.b, d.stream));
       launches += 1;
     } else {
@@ -1290,7 +1293,7 @@ int psa_gpu_pseudomode(void* vctx, double zre, double zim, const double* q0, dou
     // Q[:, it] = q  (modes.jl:236; the start vector while the slot is fresh, then the buffer selected by the parity)
     const double2* qcur = it == 1 ? d.q0 : ((it - 1) & 1 ? d.Q1 : d.Q0);
     basis_store_kernel<<<cgrid, 256, 0, d.stream>>>((int)n, qcur, d.basis + (size_t)(it - 1) * n);
-    launch_solve(sp, 1, d.num_sms, d.stream);
+    launch_solve_auto(sp, 1, d.num_sms, d.stream);
     launch_lanczos(lp, 1, d.stream);
     PSA_CUDA(cudaGetLastError());
     PSA_CUDA(cudaMemcpyAsync(&point, d.slot_point, sizeof(int), cudaMemcpyDeviceToHost, d.stream));
@@ -1354,7 +1357,7 @@ int psa_gpu_apply_resolvent(void* vctx, const double* z, int ns, const double* Q
                                              d.active, d.W, d.state);
   EventPair& ep = event_pair(d, 0);
   PSA_CUDA(cudaEventRecord(ep.a, d.stream));
-  launch_solve(solve_params(ctx, d), ns, d.num_sms, d.stream);
+  launch_solve_auto(solve_params(ctx, d), ns, d.num_sms, d.stream);
   PSA_CUDA(cudaEventRecord(ep.b, d.stream));
   store_slots_kernel<<<ns, 256, 0, d.stream>>>(ctx->n, ctx->n_pad, d.Wv, dV);
   PSA_CUDA(cudaGetLastError());
