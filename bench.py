@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 METRIC = "resolvent-norm grid points/sec"
 UNIT = "points/s"
 FP64_PEAK_FILE = os.path.join(ROOT, "profiles", "r01_fp64_gemm_peak.json")
-NCU_METRICS_FILE = "r01_ncu_metrics.json"
+NCU_METRICS_FILE = "r02_ncu_metrics.json"
 
 
 def log(*a):
@@ -387,6 +387,15 @@ def run_ours(args):
     h2d = n * n * 16 + (lx + lyl) * 8 + n * 16
     d2h = lx * lyl * (8 + 4)
 
+    # latency of ONE sparse solve launch (8 shifts = a lone 8-wide panel): the quantity that bounds the tail ticks and
+    # strong scaling over many GPUs (the library picks the cluster-pipelined kernel for it)
+    lone_ms = None
+    if rank == 0:
+        z8 = (x[:8] + 1j * y[0]).astype(np.complex128)
+        Q8 = np.tile(q0, (8, 1))
+        for _ in range(3):
+            ctx.apply_resolvent(z8, Q8)
+            lone_ms = ctx.last_stats()["solve_ms"] if lone_ms is None else min(lone_ms, ctx.last_stats()["solve_ms"])
     if rank == 0 and world == 1 and args.dump_iters:
         np.save(args.dump_iters, d_it.t().cpu().numpy())
     if rank == 0:
@@ -421,7 +430,7 @@ def run_ours(args):
                     "steps": e2e_steps, "ms_per_step": e2e_ms, "bitwise_equal_to_resident": same,
                     "call": "PsaGpu.set_matrix(T_host) + PsaGpu.grid(x, y, q0) per rank (C ABI psa_gpu_set_matrix + psa_gpu_grid)"},
             "gpu_launches": int(stats_acc["total_launches"]),
-            "roofline": {"bound": "tensor", "kernel": "psa::solve_kernel (FP64 DMMA multi-shift triangular solves)",
+            "roofline": {"bound": "tensor", "kernel": "psa::solve_deep_kernel (FP64 DMMA multi-shift triangular solves; sparse ticks: sparse / cluster variants)",
                          "achieved": achieved, "peak": pk, "unit": "TFLOP/s", "frac": achieved / pk,
                          "peak_source": "measured on this pool: cuBLAS ZGEMM 4096^3 sustained, profiles/r01_fp64_gemm_peak.json "
                                         "(MEASURED_PEAKS.json holds no FP64 figure; raw DMMA issue peak 37.2)",
@@ -430,7 +439,8 @@ def run_ours(args):
                          "whole_step_tflops": stats_acc["flops"] / (ms_total * 1e-3) * 1e-12, "traffic": traffic,
                          "traffic_note": traffic_note},
             "lanczos": {"mean_iters": float(counts[2] / max(counts[3], 1)), "nonconverged": int(counts[0]),
-                        "fallback": int(counts[1]), "ticks_per_step": stats_acc["ticks"] / args.steps},
+                        "fallback": int(counts[1]), "ticks_per_step": stats_acc["ticks"] / args.steps,
+                        "lone_panel_solve_ms": lone_ms},
             "schur_s": schur_s, "schur": how, "bcast_s": bcast_s, "algo": state["algo"],
         }
         parity_fail = False

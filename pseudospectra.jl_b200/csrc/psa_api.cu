@@ -71,8 +71,8 @@ struct Device {
   size_t T_cap = 0, pack_cap = 0, diag_cap = 0;
   double2* diagT = nullptr;  // eigenvalues (diagonal of T), for the scheduling-order predictor
   // scheduling order
-  float *key_in = nullptr, *key_out = nullptr;
-  int *ord_in = nullptr, *ord_out = nullptr;
+  float *key_in = nullptr, *key_out = nullptr, *key_static = nullptr;
+  int *ord_in = nullptr, *ord_out = nullptr, *prog = nullptr;
   void* sort_tmp = nullptr;
   size_t ord_cap = 0, sort_tmp_bytes = 0;
   // slots
@@ -199,7 +199,7 @@ void free_slots(Device& d) {
 void free_device(Device& d) {
   cudaSetDevice(d.dev);
   free_slots(d);
-  void* ptrs[] = {d.diagT, d.key_in, d.key_out, d.ord_in, d.ord_out, d.sort_tmp, d.T,     d.packA, d.packB,
+  void* ptrs[] = {d.key_static, d.prog, d.diagT, d.key_in, d.key_out, d.ord_in, d.ord_out, d.sort_tmp, d.T,     d.packA, d.packB,
                   d.state, d.counts, d.scratch64, d.x,    d.y,       d.Z,        d.q0,    d.row_batch, d.iters,
                   d.Zfull, d.itfull, d.post,      d.basis, d.yvec, d.Tp, d.Twork, d.proj_sel, d.proj_start, d.proj_rot};
   for (void* p : ptrs)
@@ -429,6 +429,8 @@ int run_grid(Context* ctx, const GridArgs& g, const std::vector<const int*>& row
   std::vector<int> rows(ng), P(ng);
   std::vector<const int*> order(ng, nullptr);
   std::vector<TickState> ts(ng);
+  std::vector<int> dyn_stride(ng, 0);   // lattice stride of the dynamic queue order (0: static order)
+  std::vector<long long> started(ng, 0);  // host view of the points started so far (exact mode: from the published counts)
   double launches = 0;
   for (int i = 0; i < ng; ++i) {
     Device& d = ctx->devs[i];
@@ -439,7 +441,7 @@ int run_grid(Context* ctx, const GridArgs& g, const std::vector<const int*>& row
       if ((rc = ensure_slots(ctx, d, slot_capacity(ctx, d, P[i]), hist))) return rc;
       PSA_CUDA(cudaMemsetAsync(d.slot_point, 0xff, (d.W + 1) * sizeof(int), d.stream));
     }
-    PSA_CUDA(cudaMemsetAsync(d.state, 0, 4 * sizeof(int), d.stream));
+    PSA_CUDA(cudaMemsetAsync(d.state, 0, 8 * sizeof(int), d.stream));
     PSA_CUDA(cudaMemsetAsync(d.counts, 0, PSA_NCOUNTS * sizeof(unsigned long long), d.stream));
     d.host_state[0] = 0;
     d.host_state[1] = 0;
@@ -451,12 +453,28 @@ int run_grid(Context* ctx, const GridArgs& g, const std::vector<const int*>& row
         d.ord_cap = 0;
         if ((rc = dev_alloc(ctx, &d.key_in, (size_t)P[i]))) return rc;
         if ((rc = dev_alloc(ctx, &d.key_out, (size_t)P[i]))) return rc;
+        if ((rc = dev_alloc(ctx, &d.key_static, (size_t)P[i]))) return rc;
         if ((rc = dev_alloc(ctx, &d.ord_in, (size_t)P[i]))) return rc;
         if ((rc = dev_alloc(ctx, &d.ord_out, (size_t)P[i]))) return rc;
+        if ((rc = dev_alloc(ctx, &d.prog, (size_t)P[i]))) return rc;
         d.ord_cap = (size_t)P[i];
       }
-      predict_kernel<<<(P[i] + 255) / 256, 256, 0, d.stream>>>(P[i], rows[i], i, ng, d.x, d.y, d.diagT, ctx->n, d.key_in,
-                                                               d.ord_in);
+      // dynamic queue order (see rekey_kernel): only worth its two small launches per tick when ticks are heavy
+      const bool dynamic = !getenv("PSA_STATIC_ORDER") && 8.0 * ctx->n * (double)ctx->n * d.W / 2.5e10 >= 3.0;
+      if (dynamic) {
+        dyn_stride[i] = std::max(1, (int)std::sqrt((double)P[i] / (0.5 * d.W)));
+        PSA_CUDA(cudaMemsetAsync(d.prog, 0, (size_t)P[i] * sizeof(int), d.stream));
+        PSA_CUDA(cudaMemsetAsync(d.scratch64 + 3, 0, sizeof(unsigned long long), d.stream));
+      }
+      predict_kernel<<<(P[i] + 255) / 256, 256, 0, d.stream>>>(P[i], rows[i], i, ng, d.x, d.y, d.diagT, ctx->n,
+                                                               dynamic ? d.key_static : d.key_in, d.ord_in,
+                                                               dynamic ? reinterpret_cast<unsigned*>(d.scratch64 + 3) : nullptr);
+      if (dynamic) {  // first order: the lattice, then the static keys
+        RekeyParams rp{P[i], rows[i], g.lx, dyn_stride[i], d.prog, d.key_static, reinterpret_cast<unsigned*>(d.scratch64 + 3),
+                       d.key_in, d.ord_in, d.state};
+        rekey_kernel<<<(P[i] + 255) / 256, 256, 0, d.stream>>>(rp);
+        launches += 1;
+      }
       size_t need = 0;
       cub::DeviceRadixSort::SortPairsDescending(nullptr, need, d.key_in, d.key_out, d.ord_in, d.ord_out, P[i], 0, 32,
                                                 d.stream);
@@ -524,6 +542,7 @@ int run_grid(Context* ctx, const GridArgs& g, const std::vector<const int*>& row
     sp.active = d.active;
     sp.fresh = d.fresh;
     sp.state = d.state;
+    sp.prog = dyn_stride[i] ? d.prog : nullptr;
     sp.host_state = d.host_state_dev;
     sp.tick = tick;
     sched_kernel<<<1, 1024, 0, d.stream>>>(sp);
@@ -607,8 +626,19 @@ int run_grid(Context* ctx, const GridArgs& g, const std::vector<const int*>& row
     lp.Z = Zout[i];
     lp.iters = itout[i];
     lp.counts = d.counts;
+    lp.prog = dyn_stride[i] ? d.prog : nullptr;
     launch_lanczos(lp, bound, d.stream);
     launches += 1;
+    if (dyn_stride[i] && started[i] < P[i]) {
+      // points are still waiting: re-key them with the progress of the lattice points around them and re-sort
+      RekeyParams rp{P[i], rows[i], g.lx, dyn_stride[i], d.prog, d.key_static, reinterpret_cast<unsigned*>(d.scratch64 + 3),
+                     d.key_in, d.ord_in, d.state};
+      rekey_kernel<<<(P[i] + 255) / 256, 256, 0, d.stream>>>(rp);
+      size_t need = d.sort_tmp_bytes;
+      PSA_CUDA(cub::DeviceRadixSort::SortPairsDescending(d.sort_tmp, need, d.key_in, d.key_out, d.ord_in, d.ord_out, P[i],
+                                                         0, 32, d.stream));
+      launches += 2;
+    }
     launch_sched(i, k + 1);
     PSA_CUDA(cudaGetLastError());
     return PSA_OK;
@@ -635,6 +665,8 @@ int run_grid(Context* ctx, const GridArgs& g, const std::vector<const int*>& row
         t.pub = tick;
         t.pub_active = (int)(h0 & 0xffffffffu);
         t.pub_fresh = (unsigned)(h1 >> 32) == tick ? (int)(h1 & 0xffffffffu) : -1;
+        // points started so far, as far as the host can tell (a stale value only costs a few extra re-sorts)
+        if (t.pub_fresh >= 0) started[i] += t.pub_fresh;
         t.bound = std::min(t.bound, (t.pub_active + APAD - 1) / APAD * APAD);
         progressed = true;
         if (t.pub_active == 0) {  // nothing active and the queue is empty: this device is finished
@@ -930,7 +962,7 @@ int psa_gpu_init(int ngpus, const int* device_ids, void** out) {
     d.num_sms = prop.multiProcessorCount;
     bool ok = cudaSetDevice(d.dev) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaMalloc((void**)&d.state, 4 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&d.state, 8 * sizeof(int)) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&d.counts, PSA_NCOUNTS * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&d.scratch64, 4 * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaHostAlloc((void**)&d.host_state, 2 * sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess;
@@ -1286,6 +1318,7 @@ int psa_gpu_pseudomode(void* vctx, double zre, double zim, const double* q0, dou
   lp.Z = d.Z;
   lp.iters = d.iters;
   lp.counts = d.counts;
+  lp.prog = nullptr;
   const SolveParams sp = solve_params(ctx, d);
   int l = 0, point = 0;
   const int cgrid = (int)std::min<size_t>((n + 255) / 256, 4 * (size_t)d.num_sms);

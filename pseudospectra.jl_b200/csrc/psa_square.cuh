@@ -93,7 +93,8 @@ __global__ void diag_kernel(const double2* __restrict__ T, long long ldt, int n,
 __global__ void __launch_bounds__(256) predict_kernel(int P, int rows_local, int row0, int row_step,
                                                        const double* __restrict__ x, const double* __restrict__ y,
                                                        const double2* __restrict__ diag, int n,
-                                                       float* __restrict__ key, int* __restrict__ val) {
+                                                       float* __restrict__ key, int* __restrict__ val,
+                                                       unsigned* __restrict__ key_max_bits) {
   __shared__ double2 ev[256];
   const int p = blockIdx.x * 256 + threadIdx.x;
   double zx = 0.0, zy = 0.0;
@@ -116,7 +117,48 @@ __global__ void __launch_bounds__(256) predict_kernel(int P, int rows_local, int
   if (p < P) {
     key[p] = (float)best;
     val[p] = p;
+    if (key_max_bits) atomicMax(key_max_bits, __float_as_uint((float)best));  // non-negative floats order like their bits
   }
+}
+
+// ---- dynamic queue order -----------------------------------------------------------------------------------
+// The static predictor (distance to the spectrum) is only a heuristic: for strongly non-normal matrices the iteration
+// count follows the resolvent norm, not the distance.  But iteration counts are spatially smooth, and the grid itself
+// tells us what they are as it is computed: a coarse LATTICE of points (stride s in both directions) is queued first,
+// and every tick the not-yet-started points are re-keyed with the progress of the lattice points around them --
+// iterations so far for a running one, the final count for a finished one -- so the neighbourhood of slow points is
+// scheduled early and the grid does not end in a tail of sparse ticks.  Ties are broken by the static key.
+// Only the ORDER of the work changes; every point's result is independent of it.
+struct RekeyParams {
+  int P, rows_local, lx, s;      // local points, local rows, columns, lattice stride
+  const int* prog;               // per point: 0 = not started, else iterations so far (final count when finished)
+  const float* key_static;
+  const unsigned* key_max_bits;
+  float* key;                    // out
+  int* val;                      // out: point index
+  int* state;                    // [0] started so far, [4] <- [0]: queue positions restart at 0 after the re-sort
+};
+
+__global__ void __launch_bounds__(256) rekey_kernel(RekeyParams R) {
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p == 0) R.state[4] = R.state[0];
+  if (p >= R.P) return;
+  R.val[p] = p;
+  if (R.prog[p] > 0) {  // started (or finished): sorts behind every waiting point
+    R.key[p] = -1.0f;
+    return;
+  }
+  const int jr = p % R.rows_local, k = p / R.rows_local, s = R.s;
+  const float stat = 0.999f * R.key_static[p] / fmaxf(__uint_as_float(*R.key_max_bits), 1e-30f);
+  if (jr % s == 0 && k % s == 0) {  // a lattice point itself: first in line
+    R.key[p] = 1.0e9f + stat;
+    return;
+  }
+  const int j0 = jr / s * s, k0 = k / s * s;
+  const int j1 = min(j0 + s, (R.rows_local - 1) / s * s), k1 = min(k0 + s, (R.lx - 1) / s * s);
+  const int m = max(max(R.prog[k0 * R.rows_local + j0], R.prog[k0 * R.rows_local + j1]),
+                    max(R.prog[k1 * R.rows_local + j0], R.prog[k1 * R.rows_local + j1]));
+  R.key[p] = (float)m + stat;
 }
 
 // ---- the solve kernel ---------------------------------------------------------------------------------
@@ -677,7 +719,9 @@ struct SchedParams {
   int* slot_batch;
   int* active;        // out, padded with W (the scratch slot) to a multiple of APAD
   int* fresh;         // out, list of newly filled slots (the HessQR path factorises those)
-  int* state;         // [0]=next_point [1]=n_active [2]=n_fresh  (device)
+  int* state;         // [0]=points started so far [1]=n_active [2]=n_fresh [3]=live ticks [4]=value of [0] at the last
+                      // re-sort of the queue (queue position of the next point = [0] - [4])
+  int* prog;          // nullable: per point progress, set to 1 when the point gets a slot (dynamic queue order)
   unsigned long long* host_state;  // mapped pinned mirror: [0] = (tick << 32) | n_active, [1] = (tick << 32) | n_fresh
   unsigned tick;      // sequence number of this tick (1, 2, ...)
 };
@@ -715,18 +759,19 @@ __global__ void __launch_bounds__(1024) sched_kernel(SchedParams S) {
   const int tid = threadIdx.x;
   const int C = (S.W + 1023) / 1024;
   const int lo = min(S.W, tid * C), hi = min(S.W, lo + C);
-  const int head = S.state[0];
+  const int started = S.state[0], head = started - S.state[4];
   int idle = 0;
   for (int i = lo; i < hi; ++i) idle += (S.slot_point[i] < 0);
   int rank = block_exscan_1024(idle, wsum, &total_s);
   const int total_idle = total_s;
-  const int n_fresh = max(0, min(total_idle, S.P - head));
+  const int n_fresh = max(0, min(total_idle, S.P - started));
   int act = 0;
   for (int i = lo; i < hi; ++i) {
     if (S.slot_point[i] < 0) {
       const int qpos = head + rank;
-      if (qpos < S.P) {
+      if (rank < n_fresh) {
         const int p = S.order ? S.order[qpos] : qpos;
+        if (S.prog) S.prog[p] = 1;
         const int jr = p % S.rows_local, k = p / S.rows_local;
         const int j = S.row0 + jr * S.row_step;
         S.slot_point[i] = p;
@@ -751,7 +796,7 @@ __global__ void __launch_bounds__(1024) sched_kernel(SchedParams S) {
   const int padded = (n_active + APAD - 1) / APAD * APAD;
   for (int i = n_active + tid; i < padded; i += 1024) S.active[i] = S.W;
   if (tid == 0) {
-    S.state[0] = head + n_fresh;
+    S.state[0] = started + n_fresh;
     S.state[1] = n_active;
     S.state[2] = n_fresh;
     if (n_active > 0) S.state[3] += 1;  // live ticks so far
@@ -835,6 +880,7 @@ struct LanczosParams {
   double* Z;          // local point order
   int* iters;         // nullable
   unsigned long long* counts;  // PSA_COUNT_*
+  int* prog;          // nullable: per point iterations so far (dynamic queue order)
 };
 
 constexpr int LZ_THREADS = 256;
@@ -962,6 +1008,7 @@ __global__ void __launch_bounds__(LZ_THREADS) lanczos_kernel(LanczosParams L) {
         const int p = L.slot_point[slot];
         L.Z[p] = 1.0 / sqrt(sigma);
         if (L.iters) L.iters[p] = l;
+        if (L.prog) L.prog[p] = l;
         L.slot_point[slot] = -1;
         if (!conv) atomicAdd(&L.counts[0], 1ull);  // incl. fallback points (compute.jl:654-656 leaves lancz_converged false)
         if (failed) atomicAdd(&L.counts[1], 1ull);
@@ -972,6 +1019,7 @@ __global__ void __launch_bounds__(LZ_THREADS) lanczos_kernel(LanczosParams L) {
         L.slot_iter[slot] = l;
         L.slot_beta[slot] = beta;
         L.slot_sel[slot] = sel ^ 1;
+        if (L.prog) L.prog[L.slot_point[slot]] = l + 1;
       }
     }
   }
@@ -1112,6 +1160,7 @@ __global__ void __launch_bounds__(LZW_WARPS * 32) lanczos_warp_kernel(LanczosPar
       const int p = L.slot_point[slot];
       L.Z[p] = 1.0 / sqrt(sigma);
       if (L.iters) L.iters[p] = l;
+      if (L.prog) L.prog[p] = l;
       L.slot_point[slot] = -1;
       if (!conv) atomicAdd(&L.counts[0], 1ull);
       if (failed) atomicAdd(&L.counts[1], 1ull);
@@ -1122,6 +1171,7 @@ __global__ void __launch_bounds__(LZW_WARPS * 32) lanczos_warp_kernel(LanczosPar
       L.slot_iter[slot] = l;
       L.slot_beta[slot] = beta;
       L.slot_sel[slot] = sel ^ 1;
+      if (L.prog) L.prog[L.slot_point[slot]] = l + 1;
     }
   }
 }

@@ -116,7 +116,10 @@ if "c5" in which:  # real Toeplitz n=8000 'triangle' symbol, 512x512 + zoom on t
     axz = [ax[0] + 0.25 * (ax[1] - ax[0]), ax[0] + 0.5 * (ax[1] - ax[0]), 0.25 * ax[3], 0.5 * ax[3]]
     xz, yz, nmz = hc._grid(axz, 512, True, False)
     t0 = time.time(); Zz, itz, cz, _ = g.grid(xz, yz, q0); dz = time.time() - t0
+    stz = g.last_stats()
     out["c5_zoom_recompute"] = {"ax": axz, "seconds": dz, "points_per_s": len(xz) * len(yz) / dz, "mean_iters": float(cz[2] / cz[3]),
+                                "max_iters": int(itz.max()), "ticks": stz["ticks"], "tflops_whole": stz["flops"] / (dz * 1e12),
+                                "tflops_solve_kernel": stz["flops"] / (stz["solve_ms"] * 1e9),
                                 "fallback_points": int(cz[1]), **sample_check(T, xz, yz, q0, Zz, itz, nsamp=8)}
     print("c5_zoom", json.dumps(out["c5_zoom_recompute"]), flush=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs_" + "_".join(which) + ".json"), "w"), indent=1)
