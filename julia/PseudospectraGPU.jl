@@ -92,9 +92,10 @@ reference's order), `row_batch[j]` the 0-based batch of grid row j.
 """
 function psacore_gpu(T, qs::Matrix{ComplexF64}, row_batch::Vector{Int32}, x::Vector{Float64}, y::Vector{Float64};
                      tol=1e-5, maxit=99, ngpus=1, ctrlflag=nothing,
-                     thresholds=Pseudospectra.psathresholds, n_mirror::Integer=0)
+                     thresholds=Pseudospectra.psathresholds, n_mirror::Integer=0, resident::Bool=false)
     ctx = context(ngpus)
-    set_matrix!(ctx, T, thresholds) || return nothing
+    # resident=true: the context's current matrix is used as it is (e.g. right after project_gpu!)
+    resident || set_matrix!(ctx, T, thresholds) || return nothing
     lx, ly = length(x), length(y)
     counts = zeros(Int64, 4)
     algo = Ref{Cint}(0)
@@ -130,6 +131,26 @@ function psacore_gpu(T, qs::Matrix{ComplexF64}, row_batch::Vector{Int32}, x::Vec
               ctx.ptr, y, ly, lx, n_mirror, ps_tiny, Pseudospectra.smallσ, Z, ly + nm, yfull, zstats)
     st == PSA_OK || error("psa_gpu_postprocess: ", strerror(st))
     return Z, yfull, zstats, ALGO[algo[]], counts
+end
+
+"""
+    project_gpu!(ctx, T, selection, thresholds) -> Tproj or `nothing`
+
+The Givens reordering + truncation of `_maybe_project` (src/compute.jl:339-357) on the device, as a wavefront of the
+reference's own swaps.  `selection` is what the host logic of compute.jl:295-316 produced (1-based, ascending).  The
+projected matrix becomes the current matrix of the context: call the following `psacore_gpu` with `resident=true`.
+The full matrix stays resident too, so the next zoom can project again (or `selection = 1:n` restores it).
+"""
+function project_gpu!(ctx::Context, T, selection::Vector{Int}, thresholds=Pseudospectra.psathresholds)
+    set_matrix!(ctx, T, thresholds) || return nothing
+    np = length(selection)
+    sel0 = Int32.(selection .- 1)
+    Tproj = Matrix{ComplexF64}(undef, np, np)
+    st = GC.@preserve sel0 Tproj ccall((:psa_gpu_project, libpsagpu), Cint,
+              (Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{ComplexF64}, Int64), ctx.ptr, sel0, np, Tproj, np)
+    st == PSA_ERR_UNSUPPORTED && return nothing
+    st == PSA_OK || error("psa_gpu_project: ", strerror(st))
+    return UpperTriangular(Tproj)
 end
 
 """
