@@ -629,7 +629,7 @@ int run_grid(Context* ctx, const GridArgs& g, const std::vector<const int*>& row
     lp.prog = dyn_stride[i] ? d.prog : nullptr;
     launch_lanczos(lp, bound, d.stream);
     launches += 1;
-    if (dyn_stride[i] && started[i] < P[i]) {
+    if (dyn_stride[i] && started[i] < P[i] && k % 4 == 0) {  // every 4th tick: the keys move one iteration per tick
       // points are still waiting: re-key them with the progress of the lattice points around them and re-sort
       RekeyParams rp{P[i], rows[i], g.lx, dyn_stride[i], d.prog, d.key_static, reinterpret_cast<unsigned*>(d.scratch64 + 3),
                      d.key_in, d.ord_in, d.state};
