@@ -511,7 +511,7 @@ def main():
     ap.add_argument("--npts", type=int, default=400)
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="time budget of EACH CPU restatement")
-    ap.add_argument("--svd-checks", type=int, default=4, help="dense svdvals pins among the parity sample (N=1)")
+    ap.add_argument("--svd-checks", type=int, default=3, help="dense svdvals pins among the parity sample (N=1)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--dump-iters", default=None, help="save the per-point Lanczos iteration counts (npy), N=1 only")
     args = ap.parse_args()

@@ -454,21 +454,27 @@ __host__ __device__ constexpr int deep_threads(int cw) { return cw * 32 + 32; }
 // position e ^ (4 * (s & 1)).  A quarter-warp of a B-fragment LDS.128 covers rows (s, s+1) x four consecutive elements:
 // the two rows then use complementary halves of the 32 banks -- conflict-free like the 320-byte padded rows of
 // solve_kernel, with 8 % smaller stages (deeper rings in the same shared memory).
+// (PAD = true keeps the 320-byte padded rows instead: measured 1 % faster for the full 32-wide launch -- 72.1 against
+// 73.0 ms, L2 hit rate 63.4 against 61.1 % -- so the full variant pads and the sparse / cluster variants, which want the
+// deepest possible ring, swizzle.)
 constexpr int XROW_D = KC * 16;
-__host__ __device__ constexpr int deep_stage_bytes(int nsv) { return TILE_BYTES + nsv * XROW_D; }
-template <int NSV, int S>
-__host__ __device__ constexpr int deep_smem() { return S * deep_stage_bytes(NSV) + 128 + NSV * 16 + NSV * 8 * 2; }
+__host__ __device__ constexpr int deep_xrow(bool pad) { return pad ? XROW_BYTES : XROW_D; }
+__host__ __device__ constexpr int deep_stage_bytes(int nsv, bool pad = false) { return TILE_BYTES + nsv * deep_xrow(pad); }
+template <int NSV, int S, bool PAD = false>
+__host__ __device__ constexpr int deep_smem() { return S * deep_stage_bytes(NSV, PAD) + 128 + NSV * 16 + NSV * 8 * 2; }
 
 template <int THREADS>
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 
-template <int NSV, int S, int CW>
+template <int NSV, int S, int CW, bool PAD>
 __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
+  constexpr int XROW = deep_xrow(PAD);     // X tile row stride
+  constexpr int SWZ = PAD ? 0 : 4;         // XOR applied to the element index of odd rows
   static_assert(S >= 3 && S <= 8 && (CW == 4 || CW == 8), "ring geometry");
   constexpr int NT = NSV / 8;
   constexpr int MT = 8 / CW;              // 8-row DMMA tiles per consumer warp
   constexpr int CTHREADS = CW * 32;       // consumer threads
-  constexpr int STAGE_BYTES = deep_stage_bytes(NSV);
+  constexpr int STAGE_BYTES = deep_stage_bytes(NSV, PAD);
   extern __shared__ __align__(128) unsigned char smem[];
   const int n_active = *P.n_active;
   const int panel = blockIdx.x;
@@ -536,7 +542,7 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
       for (int seg = lane; seg < NSV * KC; seg += 32) {  // 16-byte segments: row = seg / KC
         const int s = seg / KC, part = seg % KC;
         const double2* src = (from_q ? qptr[s] : (const double2*)wptr[s]) + mem0 + part;
-        cp_async16_hint(sb + TILE_BYTES + s * XROW_D + ((part ^ ((s & 1) << 2)) << 4), src, pol_X);
+        cp_async16_hint(sb + TILE_BYTES + s * XROW + ((part ^ ((s & 1) * SWZ)) << 4), src, pol_X);
       }
       cp_async_mbar_arrive_noinc(&full_bar[stage]);
       pc.advance();
@@ -554,8 +560,8 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
 
   auto gemm_step = [&](const unsigned char* sb, int flip) {
     const double2* At = reinterpret_cast<const double2*>(sb);
-    const unsigned char* Xt = sb + TILE_BYTES + (lane >> 2) * XROW_D;
-    const int fx = flip ^ (((lane >> 2) & 1) << 2);  // memory-order flip of the plain solve + the row swizzle
+    const unsigned char* Xt = sb + TILE_BYTES + (lane >> 2) * XROW;
+    const int fx = flip ^ (((lane >> 2) & 1) * SWZ);  // memory-order flip of the plain solve + the row swizzle
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       double2 a[MT], b[NT];
@@ -563,7 +569,7 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
       for (int mt = 0; mt < MT; ++mt) a[mt] = At[(j * 8 + MT * wm + mt) * 32 + lane];
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt)
-        b[nt] = *reinterpret_cast<const double2*>(Xt + nt * 8 * XROW_D + (((4 * j + (lane & 3)) ^ fx) << 4));
+        b[nt] = *reinterpret_cast<const double2*>(Xt + nt * 8 * XROW + (((4 * j + (lane & 3)) ^ fx) << 4));
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -614,7 +620,7 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int r = 8 * ((MT * wm + mt) & 1) + (lane >> 2), sl = 8 * nt + 2 * (lane & 3) + e;
-              double2* pb = reinterpret_cast<double2*>(Xt + sl * XROW_D + ((r ^ flip ^ (e << 2)) << 4));  // sl & 1 == e
+              double2* pb = reinterpret_cast<double2*>(Xt + sl * XROW + ((r ^ flip ^ (e * SWZ)) << 4));  // sl & 1 == e
               const double2 g = *pb;
               *pb = make_double2(g.x - cre[mt][nt][e], g.y - cim[mt][nt][e]);
               cre[mt][nt][e] = 0.0;
@@ -629,8 +635,8 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
         const int s = solver ? grp : 0;
         static_assert(NSV <= GROUPS, "one 4-lane group per shift");
         const int mem0 = cons.phase ? n_pad - KC * cons.c - KC : KC * cons.c;
-        double2* xrow = reinterpret_cast<double2*>(Xt + s * XROW_D);
-        const int fs = flip ^ ((s & 1) << 2);  // flip + row swizzle of this shift's row
+        double2* xrow = reinterpret_cast<double2*>(Xt + s * XROW);
+        const int fs = flip ^ ((s & 1) * SWZ);  // flip + row swizzle of this shift's row
         const double2* At = reinterpret_cast<const double2*>(sb);
         double2 zt = zsh[s];
         if (cons.phase == 0) zt.y = -zt.y;  // adjoint system: diagonal conj(t_ii - z)
@@ -697,7 +703,7 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
 // one CTA (sparse launches) or two CTAs per SM: the register file is not the limit
 template <int NSV, int S, int CW, int OCC>
 __global__ void __launch_bounds__(deep_threads(CW), OCC) solve_deep_kernel(SolveParams P) {
-  solve_deep_body<NSV, S, CW>(P);
+  solve_deep_body<NSV, S, CW, OCC == 2>(P);  // full variant (2 CTAs per SM): padded rows; sparse variant: swizzled
 }
 
 // ---- scheduler: refill idle slots from the point queue, compact the active list -------------------------
@@ -1257,9 +1263,9 @@ inline int solve_set_attrs() {
   set(solve_kernel<32>, solve_smem(32));
   set(solve_kernel<16>, solve_smem(16));
   set(solve_kernel<8>, solve_smem(8));
-  set(solve_deep_kernel<32, DEEP_S32, 4, DEEP_OCC>, deep_smem<32, DEEP_S32>());
-  set(solve_deep_kernel<16, DEEP_S16, 4, DEEP_OCC>, deep_smem<16, DEEP_S16>());
-  set(solve_deep_kernel<8, DEEP_S8, 4, DEEP_OCC>, deep_smem<8, DEEP_S8>());
+  set(solve_deep_kernel<32, DEEP_S32, 4, DEEP_OCC>, deep_smem<32, DEEP_S32, true>());
+  set(solve_deep_kernel<16, DEEP_S16, 4, DEEP_OCC>, deep_smem<16, DEEP_S16, true>());
+  set(solve_deep_kernel<8, DEEP_S8, 4, DEEP_OCC>, deep_smem<8, DEEP_S8, true>());
   set(solve_deep_kernel<32, SPARSE_S32, 8, 1>, deep_smem<32, SPARSE_S32>());
   set(solve_deep_kernel<16, SPARSE_S16, 8, 1>, deep_smem<16, SPARSE_S16>());
   set(solve_deep_kernel<8, SPARSE_S8, 8, 1>, deep_smem<8, SPARSE_S8>());
@@ -1311,9 +1317,9 @@ inline void launch_deep(const SolveParams& sp, int width, int panels, bool spars
     return;
   }
   switch (width) {
-    case 32: solve_deep_kernel<32, DEEP_S32, 4, DEEP_OCC><<<panels, deep_threads(4), deep_smem<32, DEEP_S32>(), stream>>>(sp); break;
-    case 16: solve_deep_kernel<16, DEEP_S16, 4, DEEP_OCC><<<panels, deep_threads(4), deep_smem<16, DEEP_S16>(), stream>>>(sp); break;
-    default: solve_deep_kernel<8, DEEP_S8, 4, DEEP_OCC><<<panels, deep_threads(4), deep_smem<8, DEEP_S8>(), stream>>>(sp); break;
+    case 32: solve_deep_kernel<32, DEEP_S32, 4, DEEP_OCC><<<panels, deep_threads(4), deep_smem<32, DEEP_S32, true>(), stream>>>(sp); break;
+    case 16: solve_deep_kernel<16, DEEP_S16, 4, DEEP_OCC><<<panels, deep_threads(4), deep_smem<16, DEEP_S16, true>(), stream>>>(sp); break;
+    default: solve_deep_kernel<8, DEEP_S8, 4, DEEP_OCC><<<panels, deep_threads(4), deep_smem<8, DEEP_S8, true>(), stream>>>(sp); break;
   }
 }
 

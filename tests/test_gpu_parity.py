@@ -682,3 +682,18 @@ def test_projection_below_minlancs_uses_svd_branch(pkg, gpu):
     assert 20 <= k < 55 and out[7] == "SVD"
     svd = np.array([[po.sigmin_svd(out[5], xx + 1j * yy) for xx in out[1]] for yy in out[2]])
     assert np.max(np.abs(out[0] - svd) / svd) < 1e-9
+
+
+def test_grcar100_published_abscissa_and_radius(gpu):
+    """The one published known answer about sigma_min the reference's test-suite holds (test/radius_abscissa.jl:25-28,
+    Guglielmi & Overton 2012): Grcar(100), eps = 1e-4, abscissa 2.41276 and radius 2.85216 to 1e-5 -- checked on the GPU
+    path through the definition of the level set (see tests/test_oracle.py: check_go)."""
+    from test_oracle import check_go
+    T, eigA = po.complex_schur(po.grcar(100))
+    q0 = po.start_vector(100, 0)
+    gpu.set_matrix(T)
+
+    def gpu_sig(zs):
+        return np.array([gpu.grid(np.array([z.real]), np.array([z.imag]), q0)[0][0, 0] for z in zs])
+
+    check_go(gpu_sig)

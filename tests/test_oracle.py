@@ -204,3 +204,55 @@ def test_reference_threads_jl_self_consistency(n):
         Z1 = co.grid(T, x, y, po.start_vector(n, 99), nthreads=4)[0]
     Z1 = np.clip(Z1, po.PS_TINY, np.inf)
     assert np.linalg.norm(Z0 - Z1) / np.linalg.norm(Z0) < 1e-4
+
+
+# ---- known answers the reference's own test-suite holds (test/radius_abscissa.jl:20-28) -----------------------------
+# Grcar(100): top eigenvalue 2.2617668 (atol 1e-6); eps = 1e-4 pseudospectral abscissa 2.41276 and radius 2.85216
+# (Guglielmi & Overton 2012, atol 1e-5).  By definition alpha_eps = max{Re z : sigma_min(zI - A) <= eps}, so on the
+# vertical line Re z = alpha the minimum of sigma_min is exactly eps, and moving the line by the test's own tolerance
+# must cross the level: min sigma(alpha - 1e-5) < eps < min sigma(alpha + 1e-5).  Same for the circle |z| = rho.
+# These are published numbers about the very quantity this path computes -- the only ones the reference holds.
+GO_EPS, GO_ALPHA, GO_RHO, GO_TOPEIG = 1e-4, 2.41276, 2.85216, 2.2617668
+
+
+def go_points():
+    """Points on the abscissa line (the level set touches it on the real axis) and on the radius circle (around the
+    touching angle, located with dense SVDs), each at the published value and at +-1e-5 (the reference's atol)."""
+    A = po.grcar(100)
+    th = np.linspace(1.3272 - 0.002, 1.3272 + 0.002, 41)
+    smin = [po.sigmin_svd(A, GO_RHO * np.exp(1j * t)) for t in th]
+    t0 = th[int(np.argmin(smin))]
+    assert 0 < int(np.argmin(smin)) < 40  # an interior minimum: the touching point is inside the bracket
+    line = {d: np.array([GO_ALPHA + d + 1j * yy for yy in np.linspace(0.0, 0.004, 5)]) for d in (-1e-5, 0.0, 1e-5)}
+    circ = {d: np.array([(GO_RHO + d) * np.exp(1j * t) for t in np.linspace(t0 - 2e-4, t0 + 2e-4, 5)]) for d in (-1e-5, 0.0, 1e-5)}
+    return A, line, circ
+
+
+def check_go(sig_of):
+    """sig_of(zs) -> sigma_min at each z (any implementation under test)."""
+    A, line, circ = go_points()
+    for name, fam in (("abscissa", line), ("radius", circ)):
+        lo, mid, hi = (float(np.min(sig_of(fam[d]))) for d in (-1e-5, 0.0, 1e-5))
+        assert lo < GO_EPS < hi, (name, lo, hi)                 # the published value is right to its stated 1e-5
+        assert abs(mid / GO_EPS - 1) < 3e-4, (name, mid)         # and sigma_min there is eps to 3e-4 relative
+
+
+def test_grcar100_published_values_pin_the_svd_checker():
+    A = po.grcar(100)
+    assert abs(np.linalg.eigvals(A).imag.max() - GO_TOPEIG) < 1e-6  # test/radius_abscissa.jl:20
+    check_go(lambda zs: np.array([po.sigmin_svd(A, z) for z in zs]))
+
+
+def test_grcar100_published_values_pin_the_lanczos_oracles():
+    """Both restatements of _psa_lanczos! (numpy + LAPACK, plain C) on the Schur factor, as the reference computes it."""
+    T, eigA = po.complex_schur(po.grcar(100))
+    q0 = po.start_vector(100, 0)
+
+    def numpy_oracle(zs):
+        return np.array([po.psacore(T, q0, np.array([z.real]), np.array([z.imag]), 1)[0][0, 0] for z in zs])
+
+    def c_oracle(zs):
+        return np.array([co.grid(T, np.array([z.real]), np.array([z.imag]), q0)[0][0, 0] for z in zs])
+
+    check_go(numpy_oracle)
+    check_go(c_oracle)

@@ -51,7 +51,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 T = np.triu(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n) + np.diag(3 * rng.standard_normal(n))
 g.set_matrix(T)
 print("n", n)
-for ns in (28416, 18944, 14208, 9472, 4736, 2368, 1184, 592, 148, 8):
+NS_LIST = (18944, 9472, 8) if len(sys.argv) > 2 and sys.argv[2] == "quick" else (28416, 18944, 14208, 9472, 4736, 2368, 1184, 592, 148, 8)
+for ns in NS_LIST:
     z = 5 * (rng.standard_normal(ns) + 1j * rng.standard_normal(ns))
     Q = rng.standard_normal((ns, n)) + 1j * rng.standard_normal((ns, n))
     ref = None
