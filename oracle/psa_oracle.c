@@ -2,8 +2,10 @@
  * TEST INFRASTRUCTURE ONLY: linked/loaded by tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs -- never by the product path.
  *
- * PARITY UNPINNED by the reference's own artefacts (no Julia here, no golden vectors in the
- * reference's tests); see oracle/psa_oracle.py for what pins it instead (dense svdvals).
+ * PARITY with the Julia implementation itself is UNPINNED (no Julia here, no golden Z vectors in the
+ * reference's tests); see oracle/psa_oracle.py for what pins the oracle instead: the Guglielmi-Overton
+ * Grcar(100) values the reference's test-suite holds (test/radius_abscissa.jl:20-28), dense svdvals,
+ * and three independent restatements agreeing to 1e-14.
  *
  * Restates, with plain loops instead of BLAS/LAPACK calls:
  *   _psa_lanczos!            /root/reference/src/compute.jl:619-665
