@@ -367,6 +367,7 @@ constexpr int CL_DC8 = 18, CL_DC16 = 13, CL_DC32 = 9;
 // how many clusters of P CTAs the device can run at once (clusters need P free SMs inside ONE GPC, so this is less than
 // num_sms / P); queried once per process with the occupancy API: g_max_clusters[width index][P index]
 static int g_max_clusters[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+static bool g_cluster_broken = false;  // set when a cluster launch was refused: fall back to the single-CTA kernels
 
 template <typename K>
 inline int query_max_clusters(K* kernel, int P, int smem) {
@@ -442,11 +443,14 @@ inline void launch_solve_auto(const SolveParams& sp, int n_active, int num_sms, 
       if (cap >= 2 && panels <= g_max_clusters[i][0] && t1[i] * f2 < c) c = t1[i] * f2, P = 2;
       if (c < best) best = c, bw = widths[i], bp = P;
     }
-    if (bw && bp > 1) {
+    if (bw && bp > 1 && !g_cluster_broken) {
       const int panels = (n_active + bw - 1) / bw;
       if (bp == 4) launch_cluster<4>(sp, bw, panels, stream);
       else launch_cluster<2>(sp, bw, panels, stream);
-      return;
+      if (cudaPeekAtLastError() == cudaSuccess) return;
+      // a cluster launch can be refused (e.g. a partitioned device): same result without it, just slower
+      cudaGetLastError();
+      g_cluster_broken = true;
     }
   }
   launch_solve(sp, n_active, num_sms, stream);

@@ -697,3 +697,25 @@ def test_grcar100_published_abscissa_and_radius(gpu):
         return np.array([gpu.grid(np.array([z.real]), np.array([z.imag]), q0)[0][0, 0] for z in zs])
 
     check_go(gpu_sig)
+
+
+def test_kernel_variants_are_bit_identical(gpu, monkeypatch):
+    """The four choreographies of the solve (round-1 kernel, deep ring, sparse, cluster pipeline over 2 / 4 SMs) and the
+    three panel widths execute the same arithmetic in the same order: one operator application, bit for bit."""
+    rng = np.random.default_rng(5)
+    n, ns = 900, 21
+    T = np.triu(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n) + np.diag(3 * rng.standard_normal(n))
+    z = 5 * (rng.standard_normal(ns) + 1j * rng.standard_normal(ns))
+    Q = rng.standard_normal((ns, n)) + 1j * rng.standard_normal((ns, n))
+    gpu.set_matrix(T)
+    monkeypatch.setenv("PSA_SOLVE_FLAVOR", "shallow")
+    V0 = gpu.apply_resolvent(z, Q)
+    F = T - z[0] * np.eye(n)
+    v = sla.solve_triangular(F, sla.solve_triangular(F, Q[0], trans="C"))
+    assert np.linalg.norm(V0[0] - v) <= 1e-11 * np.linalg.norm(v)
+    monkeypatch.setenv("PSA_SOLVE_FLAVOR", "deep")
+    for width in ("8", "16", "32"):
+        monkeypatch.setenv("PSA_PANEL_WIDTH", width)
+        for cluster in ("1", "2", "4"):
+            monkeypatch.setenv("PSA_CLUSTER", cluster)
+            assert np.array_equal(gpu.apply_resolvent(z, Q), V0), (width, cluster)
