@@ -370,7 +370,7 @@ def run_ours(args):
         if rank == 0:
             Z_host = Zf.cpu().numpy()
 
-    e2e_steps = max(1, min(args.steps, 3) if args.e2e_steps is None else args.e2e_steps)  # bounded: same work per step
+    e2e_steps = max(1, min(args.steps, 2) if args.e2e_steps is None else args.e2e_steps)  # bounded: same work per step
     step_e2e()  # warm-up
     barrier()
     t0 = time.time()
@@ -510,7 +510,7 @@ def main():
     ap.add_argument("--n", type=int, default=4000, help="matrix size (default: the BASELINE workload)")
     ap.add_argument("--npts", type=int, default=400)
     ap.add_argument("--e2e-steps", type=int, default=None)
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="time budget of EACH CPU restatement")
+    ap.add_argument("--cpu-seconds", type=float, default=8.0, help="time budget of EACH CPU restatement")
     ap.add_argument("--svd-checks", type=int, default=3, help="dense svdvals pins among the parity sample (N=1)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--dump-iters", default=None, help="save the per-point Lanczos iteration counts (npy), N=1 only")
