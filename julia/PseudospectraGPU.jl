@@ -108,7 +108,7 @@ function psacore_gpu(T, qs::Matrix{ComplexF64}, row_batch::Vector{Int32}, x::Vec
                   sleep(0.05)
               end
     bigσ = 0.1 * floatmax(Float64)                        # compute.jl:475
-    st = GC.@preserve qs row_batch x y counts cell begin
+    st = GC.@preserve qs row_batch x y counts cell algo begin
         cptr = ctrlflag === nothing ? Ptr{Cint}(C_NULL) :
                (cell isa Vector ? pointer(cell) : Base.unsafe_convert(Ptr{Cint}, cell))
         # @threadcall keeps the Julia scheduler (and the watcher) alive during the blocking call
