@@ -139,6 +139,9 @@ __global__ void __cluster_dims__(P, 1, 1) __launch_bounds__(deep_threads(8), 1) 
   cluster_arrive_wait();  // every CTA's barriers exist before anybody signals across CTAs
 
   const int nblk = Pm.nblk, n_pad = Pm.n_pad, n = Pm.n;
+  // leading chunks of the plain solve that are pure padding (x = 0): their GEMM steps and diagonal steps are left out
+  // of every CTA's step sequence (see solve_deep_body)
+  const int c0 = (n_pad - n) / KC;
 
   if (warp == CW) {
     // ================= producer warp: this CTA's share of every block row =================
@@ -149,10 +152,12 @@ __global__ void __cluster_dims__(P, 1, 1) __launch_bounds__(deep_threads(8), 1) 
       for (int I = 0; I < nblk; ++I) {
         int cb, ce;
         cluster_range<P, DC>(I, rank, cb, ce);
-        const int nsteps = (ce - cb) + (is_main ? CPB : 0);
+        if (phase == 1) cb = max(cb, min(c0, ce));
+        const int cp0 = (phase == 1 && I == 0) ? min(c0, CPB) : 0;  // first diagonal chunk that is not pure padding
+        const int nsteps = (ce - cb) + (is_main ? CPB - cp0 : 0);
         for (int k = 0; k < nsteps; ++k, ++q) {
           const bool gemm = k < ce - cb;
-          const int c = gemm ? cb + k : CPB * I + (k - (ce - cb));
+          const int c = gemm ? cb + k : CPB * I + cp0 + (k - (ce - cb));
           const int stage = q % S;
           if (q >= S) mbar_wait(&empty_bar[stage], (uint32_t)(q / S - 1) & 1u);
           // What this step loads must be final: chunk c of x once main has finished block row c / 4 of this phase; the
@@ -228,6 +233,8 @@ __global__ void __cluster_dims__(P, 1, 1) __launch_bounds__(deep_threads(8), 1) 
     for (int I = 0; I < nblk; ++I, ++row) {
       int cb, ce;
       cluster_range<P, DC>(I, rank, cb, ce);
+      if (phase == 1) cb = max(cb, min(c0, ce));
+      const int cp0 = (phase == 1 && I == 0) ? min(c0, CPB) : 0;
       const int slot = row & 1;
       const uint32_t slot_parity = (uint32_t)(row >> 1) & 1u;
       // ---- accumulators: zero (first stage) or received from the previous stage ----
@@ -267,7 +274,7 @@ __global__ void __cluster_dims__(P, 1, 1) __launch_bounds__(deep_threads(8), 1) 
         continue;
       }
       // ---- main: the four diagonal steps of this block row ----
-      for (int cp = 0; cp < CPB; ++cp, ++q) {
+      for (int cp = cp0; cp < CPB; ++cp, ++q) {
         const int c = CPB * I + cp;
         const int stage = q % S;
         unsigned char* sb = smem + stage * STAGE_BYTES;

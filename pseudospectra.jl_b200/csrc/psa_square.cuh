@@ -509,6 +509,11 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
   const int nblk = P.nblk, n_pad = P.n_pad, n = P.n;
   const int steps_per_phase = (int)tiles_per_phase(nblk);
   const int total_steps = 2 * steps_per_phase;
+  // The plain solve runs bottom-up, so the rows padded up to n_pad come FIRST there: its leading c0 chunks are pure
+  // padding (x = 0 by construction).  Steps that would only multiply by those zeros, or solve for them, are skipped:
+  // they keep their slot in the ring (the barriers are exercised, nothing is loaded or computed).  n = 4000: 126 of
+  // 16 128 steps.  Adding exact zeros changes nothing, so variants that skip and variants that do not agree bit for bit.
+  const int c0 = (n_pad - n) / KC;
 
   if (warp == CW) {
     // ================= producer warp =================
@@ -519,6 +524,13 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
       const bool gemm = pc.c < CPB * pc.I;
       // the stage is free once every consumer warp released step q - S
       if (q >= S) mbar_wait(&empty_bar[stage], (uint32_t)(q / S - 1) & 1u);
+      if (pc.phase == 1 && pc.c < c0) {  // skipped step: complete the stage's full barrier without loading anything
+        mbar_arrive(&full_bar[stage]);
+        if (lane == 0) mbar_arrive(&full_bar[stage]);
+        pc.advance();
+        if (pc.I == nblk) pc = StepCursor{1, 0, 0};
+        continue;
+      }
       // the data this step loads is final once the step that produced it has been released by every consumer warp:
       //   GEMM step: X chunk c, produced by the diagonal step (c/4, c) of the same phase;
       //   diagonal step of the plain solve: its right-hand side w, produced by the adjoint phase (mirror chunk);
@@ -603,7 +615,9 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
     mbar_wait(&full_bar[stage], (uint32_t)(t / S) & 1u);
     PSA_T1(tm_wait);
 
-    if (cons.c < CPB * cons.I) {
+    if (cons.phase == 1 && cons.c < c0) {
+      // skipped step (pure padding of the plain solve)
+    } else if (cons.c < CPB * cons.I) {
       PSA_T0();
       gemm_step(sb, flip);
       PSA_T1(tm_gemm);
