@@ -336,6 +336,10 @@ SolveParams solve_params(const Context* ctx, const Device& d) {
   sp.iter = d.slot_iter;
   sp.batch = d.slot_batch;
   sp.q0 = d.q0;
+  const char* er = getenv("PSA_ROT");  // experiments only
+  sp.rot = er ? atoi(er) : 1;
+  const char* ed = getenv("PSA_DBG");
+  sp.dbg = ed ? atoi(ed) : 0;
   return sp;
 }
 

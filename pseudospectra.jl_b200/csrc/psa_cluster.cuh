@@ -311,13 +311,12 @@ __global__ void __cluster_dims__(P, 1, 1) __launch_bounds__(deep_threads(8), 1) 
             double2 d = At[((r >> 2) * 8 + (m >> 3)) * 32 + (m & 7) * 4 + (r & 3)];
             d.x -= zt.x;
             d.y -= zt.y;
-            const double inv = __drcp_rn(fma(d.x, d.x, d.y * d.y));
-            dinv[i] = make_double2(d.x * inv, -d.y * inv);
+            dinv[i] = cinv_fixed(d);
           }
 #pragma unroll
           for (int r = 0; r < KC; ++r) {
             const int ir = r >> 2, pr = r & 3;
-            double2 x = cmul(b[ir], dinv[ir]);
+            double2 x = cmul_fixed(b[ir], dinv[ir]);
             const int op = phase ? n_pad - 1 - (p0 + r) : p0 + r;
             if (op >= n) x = make_double2(0.0, 0.0);
             if (pl == pr) b[ir] = x;

@@ -27,6 +27,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a system-dependent time; test_wait never does)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
@@ -79,6 +91,14 @@ __device__ __forceinline__ void cp_async16_hint(void* smem_dst, const void* gmem
                "l"(policy)
                : "memory");
 }
+// the same with the shared-memory destination given as a 32-bit shared-window address
+__device__ __forceinline__ void cp_async16_hint_s(uint32_t smem_dst, const void* gmem_src, uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* gmem) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem) : "memory");
+}
 // order generic-proxy writes (st.global / st.shared) before later async-proxy accesses (bulk copies)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -93,6 +113,17 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // ---- complex helpers (double2 = (re, im)) ---------------------------------------------------------
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
   return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// The diagonal-block solves of the square path exist in several choreographies that must agree bit for bit: their
+// pivot arithmetic is spelled with explicit roundings, so that the compiler's choice of which product of
+// a.x*b.x - a.y*b.y to fuse cannot differ between them.
+__device__ __forceinline__ double2 cmul_fixed(double2 a, double2 b) {
+  return make_double2(__fma_rn(a.x, b.x, -__dmul_rn(a.y, b.y)), __fma_rn(a.x, b.y, __dmul_rn(a.y, b.x)));
+}
+// 1 / d for the pivot d = t_ii - z
+__device__ __forceinline__ double2 cinv_fixed(double2 d) {
+  const double inv = __drcp_rn(__fma_rn(d.x, d.x, __dmul_rn(d.y, d.y)));
+  return make_double2(__dmul_rn(d.x, inv), -__dmul_rn(d.y, inv));
 }
 // a -= b * c
 __device__ __forceinline__ void cmsub(double2& a, double2 b, double2 c) {

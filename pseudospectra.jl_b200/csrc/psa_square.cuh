@@ -176,6 +176,8 @@ struct SolveParams {
   const int* iter;     // per-slot completed Lanczos iterations: 0 = fresh slot, q is still the start vector
   const int* batch;    // per-slot start-vector index (row batch, compute.jl:199-208)
   const double2* q0;   // [nbatch][n_pad] start vectors, zero padded
+  int rot;             // lane-solve kernels: rotation of the row-group ownership per block row (experiments; default 1)
+  int dbg;             // experiments
 };
 
 struct StepCursor {
@@ -377,13 +379,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 4) solve_kernel(SolveParams P) 
           double2 d = At[((r >> 2) * 8 + (m >> 3)) * 32 + (m & 7) * 4 + (r & 3)];
           d.x -= zt.x;
           d.y -= zt.y;
-          const double inv = __drcp_rn(fma(d.x, d.x, d.y * d.y));
-          dinv[i] = make_double2(d.x * inv, -d.y * inv);
+          dinv[i] = cinv_fixed(d);
         }
 #pragma unroll
         for (int r = 0; r < KC; ++r) {  // forward substitution in processing order; pivot r lives on lane r & 3
           const int ir = r >> 2, pr = r & 3;
-          double2 x = cmul(b[ir], dinv[ir]);
+          double2 x = cmul_fixed(b[ir], dinv[ir]);
           const int op = cons.phase ? n_pad - 1 - (p0 + r) : p0 + r;
           if (op >= n) x = make_double2(0.0, 0.0);
           if (pl == pr) b[ir] = x;
@@ -460,36 +461,58 @@ __host__ __device__ constexpr int deep_threads(int cw) { return cw * 32 + 32; }
 constexpr int XROW_D = KC * 16;
 __host__ __device__ constexpr int deep_xrow(bool pad) { return pad ? XROW_BYTES : XROW_D; }
 __host__ __device__ constexpr int deep_stage_bytes(int nsv, bool pad = false) { return TILE_BYTES + nsv * deep_xrow(pad); }
-template <int NSV, int S, bool PAD = false>
-__host__ __device__ constexpr int deep_smem() { return S * deep_stage_bytes(NSV, PAD) + 128 + NSV * 16 + NSV * 8 * 2; }
+// NP panels per CTA share the T tile of a stage; every panel has its own X tile, shifts and pointer tables
+template <int NSV, int S, bool PAD = false, int NP = 1>
+__host__ __device__ constexpr int deep_smem() {
+  return S * (TILE_BYTES + NP * NSV * deep_xrow(PAD)) + 256 + NP * (NSV * 16 + NSV * 8 * 2);
+}
 
 template <int THREADS>
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 
-template <int NSV, int S, int CW, bool PAD>
+template <int NSV, int S, int CW, bool PAD, int NP = 1>
 __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
   constexpr int XROW = deep_xrow(PAD);     // X tile row stride
   constexpr int SWZ = PAD ? 0 : 4;         // XOR applied to the element index of odd rows
   static_assert(S >= 3 && S <= 8 && (CW == 4 || CW == 8), "ring geometry");
+  static_assert(NP == 1 || CW == 4, "several panels per CTA: lane-solve variant only");
+  static_assert((2 + NP) * S * 8 <= 256, "mbarrier block");
   constexpr int NT = NSV / 8;
   constexpr int MT = 8 / CW;              // 8-row DMMA tiles per consumer warp
-  constexpr int CTHREADS = CW * 32;       // consumer threads
-  constexpr int STAGE_BYTES = deep_stage_bytes(NSV, PAD);
+  constexpr int CTHREADS = CW * 32;       // consumer threads of one panel
+  constexpr int NCW = CW * NP;            // consumer warps of the CTA; the producer is warp NCW
+  constexpr int XTILE = NSV * XROW;       // one panel's X tile
+  constexpr int STAGE_BYTES = TILE_BYTES + NP * XTILE;
+  // CW = 4: "lane-solve" diagonal steps (see the consumer loop).  Their right-hand side tile is laid out row-major by
+  // ROW, D[r][s ^ (r & 1)] (r = row of the chunk in processing order, s = shift of the panel, 16 B each), so that a
+  // lane that owns one shift reads / writes its 16 rows without bank conflicts and the tile serves as the B operand of
+  // the update of the rows below as it stands.
+  constexpr bool LANE_SOLVE = (CW == 4);
+  constexpr int DROW = NSV * 16;
   extern __shared__ __align__(128) unsigned char smem[];
   const int n_active = *P.n_active;
-  const int panel = blockIdx.x;
+  const int panel = blockIdx.x * NP;  // first panel of this CTA
   if (panel * NSV >= n_active) return;
+  int np_here = min(NP, (n_active - panel * NSV + NSV - 1) / NSV);  // panels of this CTA that hold active shifts
+  if (P.dbg & 1) np_here = 1;
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * STAGE_BYTES);  // 128 B reserved: full[S], empty[S]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * STAGE_BYTES);  // 256 B reserved: full[S], empty[S], xready[S][NP]
   uint64_t* empty_bar = full_bar + S;
-  double2* zsh = reinterpret_cast<double2*>(smem + S * STAGE_BYTES + 128);
-  double2** wptr = reinterpret_cast<double2**>(zsh + NSV);
-  const double2** qptr = (const double2**)(wptr + NSV);
+  uint64_t* xready_bar = empty_bar + S;
+  double2* zsh = reinterpret_cast<double2*>(smem + S * STAGE_BYTES + 256);
+  double2** wptr = reinterpret_cast<double2**>(zsh + NP * NSV);
+  const double2** qptr = (const double2**)(wptr + NP * NSV);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wm = warp;
+  const int pi = NP == 1 ? 0 : warp / CW;   // consumer warps: panel of the CTA this warp works for
+  const int wq = NP == 1 ? warp : warp % CW;
+  int wm = wq;  // row group of the block row this warp owns (lane-solve: rotates with the block row)
+  // byte offset of this warp's X tile within a stage.  Spelled with selects: for the product pi * XTILE ptxas 12.9 emits
+  // IDP.2A.LO.U16.U8, which a B200 rejects at run time ("an illegal instruction was encountered").
+  const int pxo = (pi >= 1 ? XTILE : 0) + (pi >= 2 ? XTILE : 0) + (pi >= 3 ? XTILE : 0);
+  static_assert(NP <= 4, "pxo");
 
-  if (tid < NSV) {
+  if (tid < np_here * NSV) {
     const int slot = P.active[panel * NSV + tid];
     wptr[tid] = P.Wv + (size_t)slot * P.n_pad;
     qptr[tid] = P.iter[slot] == 0 ? P.q0 + (size_t)P.batch[slot] * P.n_pad
@@ -500,11 +523,15 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1 + 32);               // producer lane 0 expect_tx + one cp.async arrival per producer lane
-      mbar_init(&empty_bar[s], CW);                  // one arrival per consumer warp
+      mbar_init(&empty_bar[s], CW * np_here);        // one arrival per consumer warp
+#pragma unroll
+      for (int k = 0; k < NP; ++k) mbar_init(&xready_bar[s * NP + k], 1);  // lane-solve diagonal steps: the owner warp publishes x
     }
     mbar_fence_init();
   }
   __syncthreads();
+  if (warp < NCW && pi >= np_here) return;  // consumer warps of a panel without active shifts
+  if (P.dbg & 8) return;
 
   const int nblk = P.nblk, n_pad = P.n_pad, n = P.n;
   const int steps_per_phase = (int)tiles_per_phase(nblk);
@@ -515,7 +542,7 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
   // 16 128 steps.  Adding exact zeros changes nothing, so variants that skip and variants that do not agree bit for bit.
   const int c0 = (n_pad - n) / KC;
 
-  if (warp == CW) {
+  if (warp == NCW) {
     // ================= producer warp =================
     const uint64_t pol_T = l2_policy_evict_last(), pol_X = l2_policy_evict_first();
     StepCursor pc{0, 0, 0};
@@ -550,13 +577,39 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
       }
       const bool from_q = !gemm && pc.phase == 0;
       const int mem0 = pc.phase ? n_pad - KC * pc.c - KC : KC * pc.c;
+      const bool dlay = LANE_SOLVE && !gemm;       // right-hand side of a lane-solve diagonal step: D layout
+      const int flipP = pc.phase ? (KC - 1) : 0;   // memory order -> processing order of the plain solve
+      for (int k = 0; k < np_here; ++k) {
+        // The tile base goes through an opaque register move: left warp-uniform, ptxas 12.9 addresses the copies as
+        // LDGSTS [R+UR+imm], which a B200 rejects at run time ("an illegal instruction was encountered").
+        uint32_t xb = smem_u32(sb + TILE_BYTES) + k * XTILE;
+        asm volatile("" : "+r"(xb));
 #pragma unroll
-      for (int seg = lane; seg < NSV * KC; seg += 32) {  // 16-byte segments: row = seg / KC
-        const int s = seg / KC, part = seg % KC;
-        const double2* src = (from_q ? qptr[s] : (const double2*)wptr[s]) + mem0 + part;
-        cp_async16_hint(sb + TILE_BYTES + s * XROW + ((part ^ ((s & 1) * SWZ)) << 4), src, pol_X);
+        for (int seg = lane; seg < NSV * KC; seg += 32) {  // 16-byte segments: row = seg / KC
+          const int s = seg / KC, part = seg % KC;
+          const double2* src = (from_q ? qptr[k * NSV + s] : (const double2*)wptr[k * NSV + s]) + mem0 + part;
+          const int pr = part ^ flipP;
+          const uint32_t dst = dlay ? xb + pr * DROW + ((s ^ (pr & 1)) << 4) : xb + s * XROW + ((part ^ ((s & 1) * SWZ)) << 4);
+          cp_async16_hint_s(dst, src, pol_X);
+        }
       }
       cp_async_mbar_arrive_noinc(&full_bar[stage]);
+      // X rows come from DRAM (every CTA streams its own vectors; nothing of them survives in L2 from one block row to
+      // the next): pull the rows of the GEMM step PF steps ahead into L2 now, so that their asynchronous copy, issued
+      // S - 1 steps ahead only, sees L2 latency.  Only rows that are already final: chunks of earlier block rows.
+      {
+        const int PF = P.dbg >> 8;
+        if (PF > 0 && gemm) {
+          int cf = pc.c + PF, If = pc.I;
+          while (cf >= CPB * If + CPB) { cf -= CPB * If + CPB; ++If; }   // step PF ahead, same phase (or past its end)
+          if (If < nblk && cf < CPB * pc.I && !(pc.phase == 1 && cf < c0)) {
+            const int memf = pc.phase ? n_pad - KC * cf - KC : KC * cf;
+            for (int k = 0; k < np_here; ++k)
+              for (int s = lane; s < 2 * NSV; s += 32)
+                prefetch_l2(reinterpret_cast<const char*>(wptr[k * NSV + (s >> 1)] + memf) + (s & 1) * 128);
+          }
+        }
+      }
       pc.advance();
       if (pc.I == nblk) pc = StepCursor{1, 0, 0};
     }
@@ -570,13 +623,19 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
 #pragma unroll
     for (int b = 0; b < NT; ++b) cre[a][b][0] = cre[a][b][1] = cim[a][b][0] = cim[a][b][1] = 0.0;
 
+  // Early probe of the NEXT step's full barrier, issued in the middle of a GEMM step's DMMA stream: by the time the
+  // step ends the answer is there, and the (normal) case "already loaded" costs no barrier round trip at the step boundary.
+  bool next_ready = false;
+  uint64_t* next_bar = nullptr;
+  uint32_t next_par = 0;
   auto gemm_step = [&](const unsigned char* sb, int flip) {
     const double2* At = reinterpret_cast<const double2*>(sb);
-    const unsigned char* Xt = sb + TILE_BYTES + (lane >> 2) * XROW;
+    const unsigned char* Xt = sb + TILE_BYTES + pxo + (lane >> 2) * XROW;
     const int fx = flip ^ (((lane >> 2) & 1) * SWZ);  // memory-order flip of the plain solve + the row swizzle
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       double2 a[MT], b[NT];
+      if (j == 2 && next_bar) next_ready = mbar_test_wait(next_bar, next_par);
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) a[mt] = At[(j * 8 + MT * wm + mt) * 32 + lane];
 #pragma unroll
@@ -602,28 +661,144 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
         for (int nt = 0; nt < NT; ++nt) dmma884(cim[mt][nt][0], cim[mt][nt][1], a[mt].y, b[nt].x);
     }
   };
+  // the same update with the B operand in the D layout of a lane-solve diagonal step (rows in processing order)
+  auto gemm_step_d = [&](const unsigned char* sb) {
+    const double2* At = reinterpret_cast<const double2*>(sb);
+    const unsigned char* Dt = sb + TILE_BYTES + pxo + (lane & 3) * DROW + (((lane >> 2) ^ (lane & 1)) << 4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double2 a[MT], b[NT];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) a[mt] = At[(j * 8 + MT * wm + mt) * 32 + lane];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) b[nt] = *reinterpret_cast<const double2*>(Dt + 4 * j * DROW + nt * 128);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma884(cre[mt][nt][0], cre[mt][nt][1], a[mt].x, b[nt].x);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma884(cim[mt][nt][0], cim[mt][nt][1], a[mt].x, b[nt].y);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const double nai = -a[mt].y;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma884(cre[mt][nt][0], cre[mt][nt][1], nai, b[nt].y);
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma884(cim[mt][nt][0], cim[mt][nt][1], a[mt].y, b[nt].x);
+    }
+  };
 
   StepCursor cons{0, 0, 0};
+  uint32_t xr_par = 0;  // lane-solve: per-stage parity of the next completion of xready_bar[stage]
 #ifdef PSA_TIMING
   long long tm_wait = 0, tm_gemm = 0, tm_diag = 0, tm_sync = 0, tm0;
+  unsigned long long gt0, gt1;
+  unsigned smid;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
 #endif
   for (int t = 0; t < total_steps; ++t) {
     const int stage = t % S;
     unsigned char* sb = smem + stage * STAGE_BYTES;
     const int flip = cons.phase ? (KC - 1) : 0;
+    if constexpr (LANE_SOLVE) wm = (wq + P.rot * cons.I + pi) & 3;  // ownership rotates: every warp solves one chunk per block row
     PSA_T0();
-    mbar_wait(&full_bar[stage], (uint32_t)(t / S) & 1u);
+    if (!next_ready) mbar_wait(&full_bar[stage], (uint32_t)(t / S) & 1u);
+    next_ready = false;
     PSA_T1(tm_wait);
 
-    if (cons.phase == 1 && cons.c < c0) {
+    if ((cons.phase == 1 && cons.c < c0) || (P.dbg & 16)) {
       // skipped step (pure padding of the plain solve)
     } else if (cons.c < CPB * cons.I) {
       PSA_T0();
+      {
+        const int t1 = t + 1, st1 = t1 % S;
+        next_bar = t1 < total_steps ? &full_bar[st1] : nullptr;
+        next_par = (uint32_t)(t1 / S) & 1u;
+      }
       gemm_step(sb, flip);
+      next_bar = nullptr;
       PSA_T1(tm_gemm);
     } else {
       PSA_T0();
       const int cp = cons.c - CPB * cons.I;  // diagonal sub-chunk 0..3
+      if constexpr (LANE_SOLVE) {
+        // Lane-solve diagonal step.  No CTA-wide synchronisation: the warp that owns rows 16cp..16cp+15 solves the
+        // chunk on its own, one LANE per shift (the whole 16x16 forward substitution in registers, no shuffles), and
+        // publishes x on the stage's xready barrier; warps that own rows below wait for it and update; warps that own
+        // rows above have nothing to do and move on.  With the ownership rotating from block row to block row every
+        // warp pays one solve and, on average, 1.5 updates per block row, and the four warps pass through the four
+        // diagonal steps skewed by up to a ring, overlapping each other's solves with GEMM steps.
+        // Same arithmetic per shift and row, in the same order, as the four-lanes-per-shift version: bit-identical.
+        unsigned char* Dt = sb + TILE_BYTES + pxo;
+        uint64_t* xbar = &xready_bar[stage * NP + pi];
+        const uint32_t xpar = (xr_par >> stage) & 1u;
+        xr_par ^= 1u << stage;
+        if (wm == cp) {
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int r = 8 * mt + (lane >> 2), sl = 8 * nt + 2 * (lane & 3) + e;
+                double2* pb = reinterpret_cast<double2*>(Dt + r * DROW + ((sl ^ (r & 1)) << 4));
+                const double2 g = *pb;
+                *pb = make_double2(g.x - cre[mt][nt][e], g.y - cim[mt][nt][e]);
+                cre[mt][nt][e] = 0.0;
+                cim[mt][nt][e] = 0.0;
+              }
+          __syncwarp();
+          if (lane < NSV && !(P.dbg & 2)) {
+            const int s = lane;
+            const double2* At = reinterpret_cast<const double2*>(sb);
+            double2 zt = zsh[pi * NSV + s];
+            if (cons.phase == 0) zt.y = -zt.y;  // adjoint system: diagonal conj(t_ii - z)
+            const int p0 = MB * cons.I + KC * cp;
+            const int mem0 = cons.phase ? n_pad - KC * cons.c - KC : KC * cons.c;
+            double2 b[KC];
+#pragma unroll
+            for (int r = 0; r < KC; ++r) b[r] = *reinterpret_cast<const double2*>(Dt + r * DROW + ((s ^ (r & 1)) << 4));
+#ifdef PSA_EXP_NOSOLVE
+            if (n < 0)
+#endif
+#pragma unroll
+            for (int r = 0; r < KC; ++r) {
+              const int m = KC * cp + r;
+              double2 d = At[((r >> 2) * 8 + (m >> 3)) * 32 + (m & 7) * 4 + (r & 3)];
+              d.x -= zt.x;
+              d.y -= zt.y;
+              const double2 dinv = cinv_fixed(d);
+              double2 x = cmul_fixed(b[r], dinv);
+              const int op = cons.phase ? n_pad - 1 - (p0 + r) : p0 + r;
+              if (op >= n) x = make_double2(0.0, 0.0);
+              b[r] = x;
+#pragma unroll
+              for (int i = r + 1; i < KC; ++i) {
+                const int m2 = KC * cp + i;
+                const double2 l = At[((r >> 2) * 8 + (m2 >> 3)) * 32 + (m2 & 7) * 4 + (r & 3)];
+                cmsub(b[i], l, x);
+              }
+            }
+            double2* op_ = wptr[pi * NSV + s] + mem0;
+#pragma unroll
+            for (int r = 0; r < KC; ++r) {
+              *reinterpret_cast<double2*>(Dt + r * DROW + ((s ^ (r & 1)) << 4)) = b[r];
+              op_[r ^ flip] = b[r];
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(xbar);  // x is in the stage's D tile (and on its way to global memory)
+        } else if (wm > cp) {
+          mbar_wait(xbar, xpar);
+          if (!(P.dbg & 4)) gemm_step_d(sb);  // rows below the chunk
+        }
+      } else {
       unsigned char* Xt = sb + TILE_BYTES;   // holds the right-hand side rows: element (row r, shift sl) at Xt[sl][r ^ flip]
       if ((MT * wm) >> 1 == cp) {
         // this warp owns (some of the) rows 16cp..16cp+15 of the block row: turn the right-hand side into rhs - acc
@@ -663,13 +838,12 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
           double2 d = At[((r >> 2) * 8 + (m >> 3)) * 32 + (m & 7) * 4 + (r & 3)];
           d.x -= zt.x;
           d.y -= zt.y;
-          const double inv = __drcp_rn(fma(d.x, d.x, d.y * d.y));
-          dinv[i] = make_double2(d.x * inv, -d.y * inv);
+          dinv[i] = cinv_fixed(d);
         }
 #pragma unroll
         for (int r = 0; r < KC; ++r) {  // forward substitution in processing order; pivot r lives on lane r & 3
           const int ir = r >> 2, pr = r & 3;
-          double2 x = cmul(b[ir], dinv[ir]);
+          double2 x = cmul_fixed(b[ir], dinv[ir]);
           const int op = cons.phase ? n_pad - 1 - (p0 + r) : p0 + r;
           if (op >= n) x = make_double2(0.0, 0.0);
           if (pl == pr) b[ir] = x;
@@ -698,6 +872,7 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
       }
       consumer_sync<CTHREADS>();  // x is in shared memory (this step's X tile) and on its way to global memory
       if (MT * wm >= 2 * (cp + 1)) gemm_step(sb, flip);  // rows below the chunk
+      }
       PSA_T1(tm_diag);
     }
     PSA_T0();
@@ -711,6 +886,10 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
   if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
     printf("[timing deep] cta %d warp %d: load-wait %lld gemm %lld diag %lld release %lld clk, %d steps\n", (int)blockIdx.x,
            warp, tm_wait, tm_gemm, tm_diag, tm_sync, total_steps);
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+  if (lane == 0 && warp == 0)
+    printf("[cta] %d sm %u start %llu end %llu wait %lld gemm %lld diag %lld\n", (int)blockIdx.x, smid, gt0, gt1, tm_wait, tm_gemm,
+           tm_diag);
 #endif
 }
 
@@ -718,6 +897,15 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
 template <int NSV, int S, int CW, int OCC>
 __global__ void __launch_bounds__(deep_threads(CW), OCC) solve_deep_kernel(SolveParams P) {
   solve_deep_body<NSV, S, CW, OCC == 2>(P);  // full variant (2 CTAs per SM): padded rows; sparse variant: swizzled
+}
+
+// NP panels per CTA, one CTA per SM: 4 NP consumer warps (NP DMMA-issuing warps per SM sub-partition) on ONE ring whose
+// T tile serves all NP panels -- a lone DMMA-issuing warp reaches only ~85 % of a sub-partition's pipe, so the more
+// warps remain when one of them is busy with a diagonal step or waits for a load, the better; and the T tile is
+// fetched once per SM and step instead of once per panel.
+template <int NSV, int S, int NP, bool PAD>
+__global__ void __launch_bounds__(deep_threads(4 * NP), 1) solve_multi_kernel(SolveParams P) {
+  solve_deep_body<NSV, S, 4, PAD, NP>(P);
 }
 
 // ---- scheduler: refill idle slots from the point queue, compact the active list -------------------------
@@ -1265,8 +1453,12 @@ inline int pick_panel_width(int n_active, int num_sms) {
 // "Sparse" launches (at most one panel per SM: grid tails, strong scaling over many GPUs, the pseudomode): one CTA per
 // SM with 8 consumer warps (four DMMA-issuing warps per sub-partition) and 6..8 stages.
 constexpr int DEEP_OCC = 2;
-constexpr int DEEP_S32 = 4, DEEP_S16 = 5, DEEP_S8 = 6;        // 2 CTAs per SM, CW = 4
+#ifndef PSA_EXP_S32
+#define PSA_EXP_S32 4
+#endif
+constexpr int DEEP_S32 = PSA_EXP_S32, DEEP_S16 = 5, DEEP_S8 = 6;        // 2 CTAs per SM, CW = 4
 constexpr int SPARSE_S32 = 6, SPARSE_S16 = 8, SPARSE_S8 = 8;  // one CTA per SM, CW = 8
+constexpr int MULTI3_S = 4, MULTI2_S = 6;                    // one CTA per SM, 3 / 2 panels of 32 per CTA
 
 inline int solve_set_attrs() {
   cudaError_t e = cudaSuccess;
@@ -1283,6 +1475,10 @@ inline int solve_set_attrs() {
   set(solve_deep_kernel<32, SPARSE_S32, 8, 1>, deep_smem<32, SPARSE_S32>());
   set(solve_deep_kernel<16, SPARSE_S16, 8, 1>, deep_smem<16, SPARSE_S16>());
   set(solve_deep_kernel<8, SPARSE_S8, 8, 1>, deep_smem<8, SPARSE_S8>());
+  set(solve_multi_kernel<32, MULTI3_S, 3, true>, deep_smem<32, MULTI3_S, true, 3>());
+  set(solve_multi_kernel<32, MULTI2_S, 2, false>, deep_smem<32, MULTI2_S, false, 2>());
+  set(solve_multi_kernel<32, 4, 1, true>, deep_smem<32, 4, true, 1>());
+  set(solve_multi_kernel<32, 4, 2, true>, deep_smem<32, 4, true, 2>());
   return e == cudaSuccess ? 0 : -1;
 }
 
@@ -1322,6 +1518,25 @@ inline int pick_deep_width(int n_active, int num_sms, int nblk) {
 }
 
 inline void launch_deep(const SolveParams& sp, int width, int panels, bool sparse, cudaStream_t stream) {
+  if (const char* em = getenv("PSA_MULTI")) {  // experiments: NP panels of 32 per CTA, one CTA per SM
+    const int np = atoi(em);
+    if (width == 32 && np == 3) {
+      solve_multi_kernel<32, MULTI3_S, 3, true><<<(panels + 2) / 3, deep_threads(12), deep_smem<32, MULTI3_S, true, 3>(), stream>>>(sp);
+      return;
+    }
+    if (width == 32 && np == 1) {
+      solve_multi_kernel<32, 4, 1, true><<<panels, deep_threads(4), deep_smem<32, 4, true, 1>(), stream>>>(sp);
+      return;
+    }
+    if (width == 32 && np == 22) {
+      solve_multi_kernel<32, 4, 2, true><<<(panels + 1) / 2, deep_threads(8), deep_smem<32, 4, true, 2>(), stream>>>(sp);
+      return;
+    }
+    if (width == 32 && np == 2) {
+      solve_multi_kernel<32, MULTI2_S, 2, false><<<(panels + 1) / 2, deep_threads(8), deep_smem<32, MULTI2_S, false, 2>(), stream>>>(sp);
+      return;
+    }
+  }
   if (sparse) {
     switch (width) {
       case 32: solve_deep_kernel<32, SPARSE_S32, 8, 1><<<panels, deep_threads(8), deep_smem<32, SPARSE_S32>(), stream>>>(sp); break;

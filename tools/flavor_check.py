@@ -30,7 +30,7 @@ for n, ns in ((64, 1), (150, 70), (333, 130), (1000, 300)):
             flavor(f, w); V1 = g.apply_resolvent(z, Q)
             same = np.array_equal(V0, V1)
             ok &= same
-            print(f"apply n={n} ns={ns} {f} width {w}: bitwise equal {same}", flush=True)
+            print(f"apply n={n} ns={ns} {f} width {w}: bitwise equal {same}" + ("" if same else f"  max rel diff {np.max(np.abs(V0 - V1)) / np.max(np.abs(V0)):.3e}"), flush=True)
 T, eigA = po.complex_schur(po.readme_matrix(150))
 x, y, _ = po.make_grid(po.vec2ax(eigA), 100, False)
 q0 = po.start_vector(150, 0)
@@ -68,5 +68,6 @@ for ns in NS_LIST:
                 g.apply_resolvent(z, Q); ms.append(g.last_stats()["solve_ms"])
             if ref is None: ref = V
             same = np.array_equal(V, ref); ok &= same
+            if not same: print(f"   max rel diff {np.max(np.abs(V - ref)) / np.max(np.abs(ref)):.3e}")
             print(f"ns={ns:6d} {f:8s} width={w:2d} panels={-(-ns//w):5d} {min(ms):8.2f} ms {8.0*n*n*ns/min(ms)*1e-9:6.2f} TF/s equal={same}", flush=True)
 print("ALL BITWISE EQUAL" if ok else "MISMATCH")
