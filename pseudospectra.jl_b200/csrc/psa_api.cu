@@ -336,10 +336,8 @@ SolveParams solve_params(const Context* ctx, const Device& d) {
   sp.iter = d.slot_iter;
   sp.batch = d.slot_batch;
   sp.q0 = d.q0;
-  const char* er = getenv("PSA_ROT");  // experiments only
-  sp.rot = er ? atoi(er) : 1;
-  const char* ed = getenv("PSA_DBG");
-  sp.dbg = ed ? atoi(ed) : 0;
+  const char* ep = getenv("PSA_PAIR");  // experiments only
+  sp.pair = ep ? atoi(ep) : 1;
   return sp;
 }
 

@@ -96,9 +96,6 @@ __device__ __forceinline__ void cp_async16_hint_s(uint32_t smem_dst, const void*
   asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "l"(policy)
                : "memory");
 }
-__device__ __forceinline__ void prefetch_l2(const void* gmem) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem) : "memory");
-}
 // order generic-proxy writes (st.global / st.shared) before later async-proxy accesses (bulk copies)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 

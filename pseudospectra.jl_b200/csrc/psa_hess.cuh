@@ -362,6 +362,152 @@ __global__ void __launch_bounds__(HW_THREADS) hess_solve_warp_kernel(HessSolvePa
   }
 }
 
+// Warp-per-slot variant for 256 < n <= 1024 (NPL = 16: n <= 512, NPL = 32: n <= 1024).  Same streaming scheme as
+// hess_solve_warp_kernel -- the vector in registers, rows of Rr / columns of Rc through a per-warp cp.async ring, no
+// block-level synchronisation -- restructured so that the code does not grow with NPL^2 and the register file holds
+// 32 elements per lane: the 32-element block that contains the pivots of the current 32 steps lives in one named
+// register pair (xe); the reciprocal diagonal travels with its row through the ring (slot element n32) instead of
+// sitting in registers; the block loop is a run-time loop, only the update over the NPL blocks is unrolled
+// (predicated on block > pivot block).  Same arithmetic per element and order as the small-n kernel.
+template <int NPL>
+struct HessBig {
+  static constexpr int THREADS = 128;               // 4 slots per CTA
+  static constexpr int DEPTH = 3;                   // rows in flight per warp
+  static size_t smem(int n) { return (size_t)(THREADS / 32) * DEPTH * ((n + 31) / 32 * 32 + 1) * sizeof(double2); }
+};
+
+template <int NPL>
+__global__ void __launch_bounds__(HessBig<NPL>::THREADS) hess_solve_big_kernel(HessSolveParams P) {
+  constexpr int DEPTH = HessBig<NPL>::DEPTH;
+  extern __shared__ __align__(16) unsigned char hbsm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int a = blockIdx.x * (HessBig<NPL>::THREADS / 32) + warp;
+  if (a >= *P.n_active) return;
+  const int slot = P.active[a];
+  const int n = P.n, n32 = (n + 31) / 32 * 32, rs = n32 + 1;  // ring row: n32 elements + the pivot's reciprocal
+  const size_t rstride = 2 * (size_t)n * n + (size_t)n32;
+  const double2* Rc = P.R + (size_t)slot * rstride;
+  const double2* Rr = Rc + (size_t)n * n;
+  const double2* rinv = Rr + (size_t)n * n;
+  const double2* q = hess_q_ptr(P, slot);
+  double2* ring = reinterpret_cast<double2*>(hbsm) + (size_t)warp * DEPTH * rs;
+  const double2 zero = make_double2(0.0, 0.0);
+  const int nblk = (n + 31) / 32;
+
+  double2 x[NPL];
+#pragma unroll
+  for (int e = 0; e < NPL; ++e) {
+    const int i = 32 * e + lane;
+    x[e] = i < n ? q[i] : zero;
+  }
+  auto get_block = [&](int b) {
+    double2 v = zero;
+#pragma unroll
+    for (int e = 0; e < NPL; ++e)
+      if (e == b) v = x[e];
+    return v;
+  };
+  auto put_block = [&](int b, double2 v) {
+#pragma unroll
+    for (int e = 0; e < NPL; ++e)
+      if (e == b) x[e] = v;
+  };
+  // ---- forward: (R^H) w = q.  After w_j is final, row j of R updates the entries k > j. ----
+  auto fetch_row = [&](int j) {  // entries k > j of row j (+ rinv[j]) -> ring slot j % DEPTH (always commits a group)
+    if (j < n) {
+      double2* dst = ring + (size_t)(j % DEPTH) * rs;
+      const int e0 = j >> 5;
+#pragma unroll
+      for (int e = 0; e < NPL; ++e) {
+        const int k = 32 * e + lane;
+        if (e >= e0 && k > j && k < n) cp_async16(dst + k, Rr + (size_t)j * n + k);
+      }
+      if (lane == 0) cp_async16(dst + n32, rinv + j);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int d = 0; d < DEPTH; ++d) fetch_row(d);
+  for (int je = 0; je < nblk; ++je) {
+    double2 xe = get_block(je);
+    const int jend = min(32, n - 32 * je);
+    for (int jl = 0; jl < jend; ++jl) {
+      const int j = 32 * je + jl;
+      cp_async_wait<DEPTH - 1>();
+      __syncwarp();
+      const double2* row = ring + (size_t)(j % DEPTH) * rs;
+      const double2 rj = row[n32];
+      const double xr = __shfl_sync(0xffffffffu, xe.x, jl), xi = __shfl_sync(0xffffffffu, xe.y, jl);
+      const double2 wj = cmul(make_double2(xr, xi), make_double2(rj.x, -rj.y));  // / conj(R[j,j])
+      if (lane == jl) xe = wj;
+      {
+        const int k = 32 * je + lane;
+        if (k > j && k < n) {
+          const double2 r = row[k];
+          cmsub(xe, make_double2(r.x, -r.y), wj);  // conj(R[j,k]) * w_j
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < NPL; ++e)
+        if (e > je) {
+          const int k = 32 * e + lane;
+          if (k < n) {
+            const double2 r = row[k];
+            cmsub(x[e], make_double2(r.x, -r.y), wj);
+          }
+        }
+      __syncwarp();
+      fetch_row(j + DEPTH);
+    }
+    put_block(je, xe);
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+  // ---- backward: R v = w.  After v_k is final, column k of R updates the entries i < k. ----
+  auto fetch_col = [&](int k) {  // entries i < k of column k (+ rinv[k]) -> ring slot k % DEPTH
+    if (k >= 0) {
+      double2* dst = ring + (size_t)(k % DEPTH) * rs;
+      const int e1 = k >> 5;
+#pragma unroll
+      for (int e = 0; e < NPL; ++e) {
+        const int i = 32 * e + lane;
+        if (e <= e1 && i < k) cp_async16(dst + i, Rc + (size_t)k * n + i);
+      }
+      if (lane == 0) cp_async16(dst + n32, rinv + k);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int d = 0; d < DEPTH; ++d) fetch_col(n - 1 - d);
+  for (int ke = nblk - 1; ke >= 0; --ke) {
+    double2 xe = get_block(ke);
+    for (int kl = min(31, n - 1 - 32 * ke); kl >= 0; --kl) {
+      const int k = 32 * ke + kl;
+      cp_async_wait<DEPTH - 1>();
+      __syncwarp();
+      const double2* col = ring + (size_t)(k % DEPTH) * rs;
+      const double2 rk = col[n32];
+      const double xr = __shfl_sync(0xffffffffu, xe.x, kl), xi = __shfl_sync(0xffffffffu, xe.y, kl);
+      const double2 vk = cmul(make_double2(xr, xi), rk);
+      if (lane == kl) xe = vk;
+      if (lane < kl) cmsub(xe, col[32 * ke + lane], vk);
+#pragma unroll
+      for (int e = 0; e < NPL; ++e)
+        if (e < ke) cmsub(x[e], col[32 * e + lane], vk);
+      __syncwarp();
+      fetch_col(k - DEPTH);
+    }
+    put_block(ke, xe);
+  }
+  cp_async_wait<0>();
+  double2* out = P.Wv + (size_t)slot * P.n_pad;
+#pragma unroll
+  for (int e = 0; e < NPL; ++e) {
+    const int i = 32 * e + lane;
+    if (i < n) out[i] = x[e];
+  }
+}
+
 struct HessTick {
   int m, n, n_pad;
   const double2* H;
@@ -388,6 +534,10 @@ inline int hess_set_attrs() {
   cudaError_t e = cudaFuncSetAttribute(hess_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(hess_solve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hess_warp_smem(32 * HW_NPL));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(hess_solve_big_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HessBig<16>::smem(512));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(hess_solve_big_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HessBig<32>::smem(1024));
   return e == cudaSuccess ? 0 : -1;
 }
 
@@ -415,8 +565,12 @@ inline int hess_launch_tick(const HessTick& t, cudaStream_t stream, cudaEvent_t 
   sp.q0 = t.q0;
   if (t.n <= 32 * HW_NPL)
     hess_solve_warp_kernel<<<(t.n_active + HW_THREADS / 32 - 1) / (HW_THREADS / 32), HW_THREADS, hess_warp_smem(t.n), stream>>>(sp);
-  else
+  else if (getenv("PSA_HESS_CTA"))  // experiments: the CTA-per-slot kernel (A/B timing)
     hess_solve_kernel<<<t.n_active, HS_THREADS, hess_solve_smem(t.n_pad), stream>>>(sp);
+  else if (t.n <= 512)
+    hess_solve_big_kernel<16><<<(t.n_active + 3) / 4, HessBig<16>::THREADS, HessBig<16>::smem(t.n), stream>>>(sp);
+  else
+    hess_solve_big_kernel<32><<<(t.n_active + 3) / 4, HessBig<32>::THREADS, HessBig<32>::smem(t.n), stream>>>(sp);
   ++launches;
   cudaEventRecord(ev_b, stream);
   return launches;

@@ -176,8 +176,7 @@ struct SolveParams {
   const int* iter;     // per-slot completed Lanczos iterations: 0 = fresh slot, q is still the start vector
   const int* batch;    // per-slot start-vector index (row batch, compute.jl:199-208)
   const double2* q0;   // [nbatch][n_pad] start vectors, zero padded
-  int rot;             // lane-solve kernels: rotation of the row-group ownership per block row (experiments; default 1)
-  int dbg;             // experiments
+  int pair;            // fuse pairs of GEMM steps whose stages have both landed (PSA_PAIR=0 switches it off: A/B timing)
 };
 
 struct StepCursor {
@@ -488,13 +487,13 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
   // lane that owns one shift reads / writes its 16 rows without bank conflicts and the tile serves as the B operand of
   // the update of the rows below as it stands.
   constexpr bool LANE_SOLVE = (CW == 4);
+  constexpr bool PAIR_STEPS = true;
   constexpr int DROW = NSV * 16;
   extern __shared__ __align__(128) unsigned char smem[];
   const int n_active = *P.n_active;
   const int panel = blockIdx.x * NP;  // first panel of this CTA
   if (panel * NSV >= n_active) return;
-  int np_here = min(NP, (n_active - panel * NSV + NSV - 1) / NSV);  // panels of this CTA that hold active shifts
-  if (P.dbg & 1) np_here = 1;
+  const int np_here = min(NP, (n_active - panel * NSV + NSV - 1) / NSV);  // panels of this CTA that hold active shifts
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * STAGE_BYTES);  // 256 B reserved: full[S], empty[S], xready[S][NP]
   uint64_t* empty_bar = full_bar + S;
@@ -531,7 +530,6 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
   }
   __syncthreads();
   if (warp < NCW && pi >= np_here) return;  // consumer warps of a panel without active shifts
-  if (P.dbg & 8) return;
 
   const int nblk = P.nblk, n_pad = P.n_pad, n = P.n;
   const int steps_per_phase = (int)tiles_per_phase(nblk);
@@ -594,22 +592,6 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
         }
       }
       cp_async_mbar_arrive_noinc(&full_bar[stage]);
-      // X rows come from DRAM (every CTA streams its own vectors; nothing of them survives in L2 from one block row to
-      // the next): pull the rows of the GEMM step PF steps ahead into L2 now, so that their asynchronous copy, issued
-      // S - 1 steps ahead only, sees L2 latency.  Only rows that are already final: chunks of earlier block rows.
-      {
-        const int PF = P.dbg >> 8;
-        if (PF > 0 && gemm) {
-          int cf = pc.c + PF, If = pc.I;
-          while (cf >= CPB * If + CPB) { cf -= CPB * If + CPB; ++If; }   // step PF ahead, same phase (or past its end)
-          if (If < nblk && cf < CPB * pc.I && !(pc.phase == 1 && cf < c0)) {
-            const int memf = pc.phase ? n_pad - KC * cf - KC : KC * cf;
-            for (int k = 0; k < np_here; ++k)
-              for (int s = lane; s < 2 * NSV; s += 32)
-                prefetch_l2(reinterpret_cast<const char*>(wptr[k * NSV + (s >> 1)] + memf) + (s & 1) * 128);
-          }
-        }
-      }
       pc.advance();
       if (pc.I == nblk) pc = StepCursor{1, 0, 0};
     }
@@ -693,6 +675,45 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
     }
   };
 
+  // two consecutive GEMM steps (stages sbA, sbB) as one unrolled stream of 8 k4 groups; stage A is released after B's
+  // first fragment loads have been issued (program order: the compiler may hoist those loads above A's last DMMAs)
+  auto gemm_pair = [&](const unsigned char* sbA, const unsigned char* sbB, int flip, uint64_t* emptyA) {
+    const int fx = flip ^ (((lane >> 2) & 1) * SWZ);
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const unsigned char* sbx = jj < 4 ? sbA : sbB;
+      const int j = jj & 3;
+      const double2* At = reinterpret_cast<const double2*>(sbx);
+      const unsigned char* Xt = sbx + TILE_BYTES + pxo + (lane >> 2) * XROW;
+      double2 a[MT], b[NT];
+      if (jj == 6 && next_bar) next_ready = mbar_test_wait(next_bar, next_par);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) a[mt] = At[(j * 8 + MT * wm + mt) * 32 + lane];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+        b[nt] = *reinterpret_cast<const double2*>(Xt + nt * 8 * XROW + (((4 * j + (lane & 3)) ^ fx) << 4));
+      if (jj == 4 && lane == 0) mbar_arrive(emptyA);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma884(cre[mt][nt][0], cre[mt][nt][1], a[mt].x, b[nt].x);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma884(cim[mt][nt][0], cim[mt][nt][1], a[mt].x, b[nt].y);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const double nai = -a[mt].y;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma884(cre[mt][nt][0], cre[mt][nt][1], nai, b[nt].y);
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma884(cim[mt][nt][0], cim[mt][nt][1], a[mt].y, b[nt].x);
+    }
+  };
+
   StepCursor cons{0, 0, 0};
   uint32_t xr_par = 0;  // lane-solve: per-stage parity of the next completion of xready_bar[stage]
 #ifdef PSA_TIMING
@@ -706,13 +727,63 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
     const int stage = t % S;
     unsigned char* sb = smem + stage * STAGE_BYTES;
     const int flip = cons.phase ? (KC - 1) : 0;
-    if constexpr (LANE_SOLVE) wm = (wq + P.rot * cons.I + pi) & 3;  // ownership rotates: every warp solves one chunk per block row
+    if constexpr (LANE_SOLVE) wm = (wq + cons.I + pi) & 3;  // ownership rotates: every warp solves one chunk per block row
+    if constexpr (LANE_SOLVE) {
+      // A run of GEMM steps (the rest of this block row's off-diagonal tiles) in a tight loop: the ring position advances
+      // by increments, nothing else is recomputed per step.  No __syncwarp before the release: mma.sync is a warp-wide
+      // instruction, so once the step's last DMMA has issued every lane's fragment loads from the stage have completed.
+      const int first = (cons.phase == 1) ? max(cons.c, c0) : cons.c;   // (skipped padding steps take the generic path)
+      if (first == cons.c && cons.c < CPB * cons.I) {
+        const int cnt = CPB * cons.I - cons.c;
+        int st = stage;
+        uint32_t par = (uint32_t)(t / S) & 1u;
+        unsigned char* sbr = sb;
+        PSA_T0();
+        const bool pairing = PAIR_STEPS && P.pair != 0;
+        for (int k = 0; k < cnt;) {
+          if (!next_ready) mbar_wait(&full_bar[st], par);
+          next_ready = false;
+          const int st1 = st + 1 == S ? 0 : st + 1;
+          const uint32_t par1 = st1 == 0 ? par ^ 1u : par;
+          unsigned char* sb1 = st1 == 0 ? smem : sbr + STAGE_BYTES;
+          // two steps as ONE instruction stream when the next stage has landed too: no barrier round trip and no drained
+          // DMMA pipe between them (the second step's first fragment loads overlap the first step's last DMMAs)
+          if (pairing && k + 1 < cnt && mbar_test_wait(&full_bar[st1], par1)) {
+            const int st2 = st1 + 1 == S ? 0 : st1 + 1;
+            next_bar = (t + k + 2 < total_steps) ? &full_bar[st2] : nullptr;
+            next_par = st2 == 0 ? par1 ^ 1u : par1;
+            gemm_pair(sbr, sb1, flip, &empty_bar[st]);
+            if (lane == 0) mbar_arrive(&empty_bar[st1]);
+            sbr = st2 == 0 ? smem : sb1 + STAGE_BYTES;
+            par = next_par;
+            st = st2;
+            k += 2;
+          } else {
+            next_bar = (t + k + 1 < total_steps) ? &full_bar[st1] : nullptr;
+            next_par = par1;
+            gemm_step(sbr, flip);
+            if (lane == 0) mbar_arrive(&empty_bar[st]);
+            sbr = sb1;
+            par = par1;
+            st = st1;
+            k += 1;
+          }
+        }
+        next_bar = nullptr;
+        PSA_T1(tm_gemm);
+        t += cnt - 1;
+        cons.c = CPB * cons.I - 1;
+        cons.advance();
+        if (cons.I == nblk) cons = StepCursor{1, 0, 0};
+        continue;
+      }
+    }
     PSA_T0();
     if (!next_ready) mbar_wait(&full_bar[stage], (uint32_t)(t / S) & 1u);
     next_ready = false;
     PSA_T1(tm_wait);
 
-    if ((cons.phase == 1 && cons.c < c0) || (P.dbg & 16)) {
+    if (cons.phase == 1 && cons.c < c0) {
       // skipped step (pure padding of the plain solve)
     } else if (cons.c < CPB * cons.I) {
       PSA_T0();
@@ -754,7 +825,7 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
                 cim[mt][nt][e] = 0.0;
               }
           __syncwarp();
-          if (lane < NSV && !(P.dbg & 2)) {
+          if (lane < NSV) {
             const int s = lane;
             const double2* At = reinterpret_cast<const double2*>(sb);
             double2 zt = zsh[pi * NSV + s];
@@ -764,9 +835,6 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
             double2 b[KC];
 #pragma unroll
             for (int r = 0; r < KC; ++r) b[r] = *reinterpret_cast<const double2*>(Dt + r * DROW + ((s ^ (r & 1)) << 4));
-#ifdef PSA_EXP_NOSOLVE
-            if (n < 0)
-#endif
 #pragma unroll
             for (int r = 0; r < KC; ++r) {
               const int m = KC * cp + r;
@@ -796,7 +864,7 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
           if (lane == 0) mbar_arrive(xbar);  // x is in the stage's D tile (and on its way to global memory)
         } else if (wm > cp) {
           mbar_wait(xbar, xpar);
-          if (!(P.dbg & 4)) gemm_step_d(sb);  // rows below the chunk
+          gemm_step_d(sb);  // rows below the chunk
         }
       } else {
       unsigned char* Xt = sb + TILE_BYTES;   // holds the right-hand side rows: element (row r, shift sl) at Xt[sl][r ^ flip]
@@ -1453,12 +1521,9 @@ inline int pick_panel_width(int n_active, int num_sms) {
 // "Sparse" launches (at most one panel per SM: grid tails, strong scaling over many GPUs, the pseudomode): one CTA per
 // SM with 8 consumer warps (four DMMA-issuing warps per sub-partition) and 6..8 stages.
 constexpr int DEEP_OCC = 2;
-#ifndef PSA_EXP_S32
-#define PSA_EXP_S32 4
-#endif
-constexpr int DEEP_S32 = PSA_EXP_S32, DEEP_S16 = 5, DEEP_S8 = 6;        // 2 CTAs per SM, CW = 4
+constexpr int DEEP_S32 = 4, DEEP_S16 = 5, DEEP_S8 = 6;        // 2 CTAs per SM, CW = 4
 constexpr int SPARSE_S32 = 6, SPARSE_S16 = 8, SPARSE_S8 = 8;  // one CTA per SM, CW = 8
-constexpr int MULTI3_S = 4, MULTI2_S = 6;                    // one CTA per SM, 3 / 2 panels of 32 per CTA
+constexpr int MULTI2_S = 6;                                   // one CTA per SM, 2 panels of 32 per CTA (experimental)
 
 inline int solve_set_attrs() {
   cudaError_t e = cudaSuccess;
@@ -1475,10 +1540,7 @@ inline int solve_set_attrs() {
   set(solve_deep_kernel<32, SPARSE_S32, 8, 1>, deep_smem<32, SPARSE_S32>());
   set(solve_deep_kernel<16, SPARSE_S16, 8, 1>, deep_smem<16, SPARSE_S16>());
   set(solve_deep_kernel<8, SPARSE_S8, 8, 1>, deep_smem<8, SPARSE_S8>());
-  set(solve_multi_kernel<32, MULTI3_S, 3, true>, deep_smem<32, MULTI3_S, true, 3>());
   set(solve_multi_kernel<32, MULTI2_S, 2, false>, deep_smem<32, MULTI2_S, false, 2>());
-  set(solve_multi_kernel<32, 4, 1, true>, deep_smem<32, 4, true, 1>());
-  set(solve_multi_kernel<32, 4, 2, true>, deep_smem<32, 4, true, 2>());
   return e == cudaSuccess ? 0 : -1;
 }
 
@@ -1518,21 +1580,8 @@ inline int pick_deep_width(int n_active, int num_sms, int nblk) {
 }
 
 inline void launch_deep(const SolveParams& sp, int width, int panels, bool sparse, cudaStream_t stream) {
-  if (const char* em = getenv("PSA_MULTI")) {  // experiments: NP panels of 32 per CTA, one CTA per SM
-    const int np = atoi(em);
-    if (width == 32 && np == 3) {
-      solve_multi_kernel<32, MULTI3_S, 3, true><<<(panels + 2) / 3, deep_threads(12), deep_smem<32, MULTI3_S, true, 3>(), stream>>>(sp);
-      return;
-    }
-    if (width == 32 && np == 1) {
-      solve_multi_kernel<32, 4, 1, true><<<panels, deep_threads(4), deep_smem<32, 4, true, 1>(), stream>>>(sp);
-      return;
-    }
-    if (width == 32 && np == 22) {
-      solve_multi_kernel<32, 4, 2, true><<<(panels + 1) / 2, deep_threads(8), deep_smem<32, 4, true, 2>(), stream>>>(sp);
-      return;
-    }
-    if (width == 32 && np == 2) {
+  if (const char* em = getenv("PSA_MULTI")) {  // experiments only: two panels of 32 per CTA, one CTA per SM, 6-stage ring
+    if (width == 32 && atoi(em) == 2) {
       solve_multi_kernel<32, MULTI2_S, 2, false><<<(panels + 1) / 2, deep_threads(8), deep_smem<32, MULTI2_S, false, 2>(), stream>>>(sp);
       return;
     }

@@ -136,10 +136,11 @@ def test_hessqr_arnoldi_projection_vs_oracle(gpu):
     assert algo == "HessQR" and _rel(Z, Zc, _floor(H)) < RTOL and np.mean(it == itc) > 0.97
 
 
-def test_hessqr_large_n_uses_block_kernel(gpu):
-    """n > 256: the vector no longer fits the warp-per-slot kernel's registers; the CTA-per-slot solve kernel runs."""
+@pytest.mark.parametrize("n", [300, 600])
+def test_hessqr_large_n_streaming_kernels(gpu, n, monkeypatch):
+    """256 < n <= 1024: warp-per-slot streaming kernel with 16 / 32 vector elements per lane (hess_solve_big_kernel);
+    PSA_HESS_CTA=1 selects the CTA-per-slot kernel (different summation order: agreement to rounding, not bit for bit)."""
     rng = np.random.default_rng(11)
-    n = 300
     H = np.triu(rng.standard_normal((n + 1, n)) + 1j * rng.standard_normal((n + 1, n)), -1)
     x, y = np.linspace(-3, 3, 5), np.linspace(-3, 3, 4)
     q0 = po.start_vector(n, 1)
@@ -147,6 +148,9 @@ def test_hessqr_large_n_uses_block_kernel(gpu):
     Z, it, counts, algo = gpu.grid(x, y, q0)
     Zc, itc, _ = co.grid(H, x, y, q0, nthreads=8)
     assert algo == "HessQR" and _rel(Z, Zc, _floor(H)) < RTOL and np.mean(it == itc) > 0.9
+    monkeypatch.setenv("PSA_HESS_CTA", "1")
+    Z2, it2, _, _ = gpu.grid(x, y, q0)
+    assert _rel(Z2, Z, _floor(H)) < 1e-9 and np.mean(it2 == it) > 0.9
 
 
 def test_random_complex_600_vs_oracle_and_svd(gpu):
@@ -703,7 +707,7 @@ def test_kernel_variants_are_bit_identical(gpu, monkeypatch):
     """The four choreographies of the solve (round-1 kernel, deep ring, sparse, cluster pipeline over 2 / 4 SMs) and the
     three panel widths execute the same arithmetic in the same order: one operator application, bit for bit."""
     rng = np.random.default_rng(5)
-    n, ns = 900, 21
+    n, ns = 900, 45
     T = np.triu(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n) + np.diag(3 * rng.standard_normal(n))
     z = 5 * (rng.standard_normal(ns) + 1j * rng.standard_normal(ns))
     Q = rng.standard_normal((ns, n)) + 1j * rng.standard_normal((ns, n))
@@ -719,3 +723,11 @@ def test_kernel_variants_are_bit_identical(gpu, monkeypatch):
         for cluster in ("1", "2", "4"):
             monkeypatch.setenv("PSA_CLUSTER", cluster)
             assert np.array_equal(gpu.apply_resolvent(z, Q), V0), (width, cluster)
+        # the full-launch instantiation (2 CTAs per SM, lane-per-shift diagonal steps) and, 32-wide, two panels per CTA
+        monkeypatch.setenv("PSA_CLUSTER", "1")
+        monkeypatch.setenv("PSA_DEEP_CW", "4")
+        assert np.array_equal(gpu.apply_resolvent(z, Q), V0), (width, "full")
+        monkeypatch.setenv("PSA_MULTI", "2")
+        assert np.array_equal(gpu.apply_resolvent(z, Q), V0), (width, "multi")
+        monkeypatch.delenv("PSA_MULTI")
+        monkeypatch.delenv("PSA_DEEP_CW")
