@@ -5,6 +5,8 @@
 // then run the inverse-Lanczos recurrence on that private triangular factor (602).  Every shift owns its own
 // R, so this path is BLAS-2 and bound by memory bandwidth (HBM / L2), not by the tensor pipe.
 #pragma once
+#include <type_traits>
+
 #include "psa_common.cuh"
 
 namespace psa {
@@ -22,6 +24,12 @@ inline long long hess_slot_capacity(int n, int num_sms) {
   const long long by_mem = (24LL << 30) / ((long long)hess_R_elems(n) * 16 + 1);
   long long w = 64LL * num_sms;
   if (w > by_mem) w = by_mem;
+  if (n > 256) {
+    // the warp-per-slot streaming kernels for large n keep 8 (n <= 512) / 4 (n <= 1024) warps resident per SM: whole
+    // waves only, a partly filled last wave costs a full one (each warp's solve is a latency-bound chain of 2n steps)
+    const long long wave = (n <= 512 ? 8LL : 4LL) * num_sms;
+    if (w >= wave) return w / wave * wave;
+  }
   return w < 64 ? 64 : w / 64 * 64;
 }
 
@@ -32,17 +40,29 @@ __device__ __forceinline__ void givens_cs(double2 f, double2 g, double& c, doubl
     s = make_double2(0.0, 0.0);
     return;
   }
-  const double ag = hypot(g.x, g.y);
-  if (f.x == 0.0 && f.y == 0.0) {
+  // The rotation is on the critical path of the sweep (one thread computes it, everybody waits), so no hypot() here:
+  // an exact power-of-two scaling to the unit range guards the squares against overflow and underflow, then
+  // c = |f| / d and s = (f / |f|) conj(g) / d with d = sqrt(|f|^2 + |g|^2) come from two reciprocal square roots.
+  const double mx = fmax(fmax(fabs(f.x), fabs(f.y)), fmax(fabs(g.x), fabs(g.y)));
+  int ex;
+  (void)frexp(mx, &ex);
+  const double sc = ldexp(1.0, -max(ex, -1000));  // (subnormal inputs: stay finite)
+  f.x *= sc;
+  f.y *= sc;
+  g.x *= sc;
+  g.y *= sc;
+  const double ag2 = fma(g.x, g.x, g.y * g.y);
+  const double af2 = fma(f.x, f.x, f.y * f.y);
+  if (af2 == 0.0) {
+    const double ia = rsqrt(ag2);
     c = 0.0;
-    s = make_double2(g.x / ag, -g.y / ag);
+    s = make_double2(g.x * ia, -g.y * ia);
     return;
   }
-  const double af = hypot(f.x, f.y);
-  const double d = hypot(af, ag);
-  c = af / d;
-  const double2 ph = make_double2(f.x / af, f.y / af);
-  const double2 cg = make_double2(g.x / d, -g.y / d);
+  const double iaf = rsqrt(af2), id = rsqrt(af2 + ag2);
+  c = af2 * iaf * id;
+  const double2 ph = make_double2(f.x * iaf, f.y * iaf);
+  const double2 cg = make_double2(g.x * id, -g.y * id);
   s = cmul(ph, cg);
 }
 
@@ -53,7 +73,7 @@ __device__ __forceinline__ void givens_cs(double2 f, double2 g, double& c, doubl
 // full_sweep = 1: :rect_qr on Hessenberg input: the reference calls qr(T1) (compute.jl:589), which also
 //   eliminates H[n+1,n]; for an upper Hessenberg matrix that is one more rotation, and R is unique up to unit row
 //   phases, which leave (R^H R) and hence sigma unchanged.
-__global__ void hess_qr_kernel(const int* __restrict__ fresh, const int* __restrict__ n_fresh, int m, int n,
+__global__ void __launch_bounds__(HQ_MAX_N) hess_qr_kernel(const int* __restrict__ fresh, const int* __restrict__ n_fresh, int m, int n,
                                const double2* __restrict__ H, const double2* __restrict__ zs,
                                double2* __restrict__ Rall, int full_sweep) {
   __shared__ double g_c[2];
@@ -78,15 +98,18 @@ __global__ void hess_qr_kernel(const int* __restrict__ fresh, const int* __restr
       carry.y -= z.y;
     }
   }
+  // H[jj+1, c] is fetched one rotation ahead (a strided read of the shared H: L2 latency off the critical path)
+  double2 bnext = (live && n > 1) ? Hc[1] : make_double2(0.0, 0.0);
   for (int jj = 0; jj < n - 1; ++jj) {
     double2 b = make_double2(0.0, 0.0);
     if (live && c >= jj) {
-      b = Hc[jj + 1];
+      b = bnext;
       if (jj + 1 == c) {
         b.x -= z.x;
         b.y -= z.y;
       }
     }
+    if (live && c >= jj + 1 && jj + 2 < m) bnext = Hc[jj + 2];
     if (c == jj) {
       double cs;
       double2 sn;
@@ -366,33 +389,37 @@ __global__ void __launch_bounds__(HW_THREADS) hess_solve_warp_kernel(HessSolvePa
 // hess_solve_warp_kernel -- the vector in registers, rows of Rr / columns of Rc through a per-warp cp.async ring, no
 // block-level synchronisation -- restructured so that the code does not grow with NPL^2 and the register file holds
 // 32 elements per lane: the 32-element block that contains the pivots of the current 32 steps lives in one named
-// register pair (xe); the reciprocal diagonal travels with its row through the ring (slot element n32) instead of
-// sitting in registers; the block loop is a run-time loop, only the update over the NPL blocks is unrolled
-// (predicated on block > pivot block).  Same arithmetic per element and order as the small-n kernel.
+// register pair (xe); the reciprocal diagonal travels with its row through the ring instead of sitting in registers;
+// the block loop is a run-time loop, only the update over the NPL blocks is unrolled (predicated on block > pivot block).
+// A step is bound by the latency of its row (fetched DEPTH - 1 steps ahead), and the rows of a triangular factor get
+// shorter: the ring is re-cut in LEVELS -- once at most 1/2, 1/4, 1/8 of the blocks remain, the same shared memory holds
+// 6, 12, 24 rows in flight instead of 3 (one drain of the ring per level).
+// Same arithmetic per element, in the same order, as the small-n kernel.
 template <int NPL>
 struct HessBig {
   static constexpr int THREADS = 128;               // 4 slots per CTA
-  static constexpr int DEPTH = 3;                   // rows in flight per warp
-  static size_t smem(int n) { return (size_t)(THREADS / 32) * DEPTH * ((n + 31) / 32 * 32 + 1) * sizeof(double2); }
+  static constexpr int DEPTH0 = 3;                  // rows in flight per warp at level 0
+  static constexpr int LEVELS = 4;
+  static int ring_elems(int n) { return DEPTH0 * ((n + 31) / 32 * 32) + 32; }
+  static size_t smem(int n) { return (size_t)(THREADS / 32) * ring_elems(n) * sizeof(double2); }
 };
 
 template <int NPL>
 __global__ void __launch_bounds__(HessBig<NPL>::THREADS) hess_solve_big_kernel(HessSolveParams P) {
-  constexpr int DEPTH = HessBig<NPL>::DEPTH;
+  using HBK = HessBig<NPL>;
   extern __shared__ __align__(16) unsigned char hbsm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int a = blockIdx.x * (HessBig<NPL>::THREADS / 32) + warp;
+  const int a = blockIdx.x * (HBK::THREADS / 32) + warp;
   if (a >= *P.n_active) return;
   const int slot = P.active[a];
-  const int n = P.n, n32 = (n + 31) / 32 * 32, rs = n32 + 1;  // ring row: n32 elements + the pivot's reciprocal
+  const int n = P.n, n32 = (n + 31) / 32 * 32, nblk = n32 / 32;
   const size_t rstride = 2 * (size_t)n * n + (size_t)n32;
   const double2* Rc = P.R + (size_t)slot * rstride;
   const double2* Rr = Rc + (size_t)n * n;
   const double2* rinv = Rr + (size_t)n * n;
   const double2* q = hess_q_ptr(P, slot);
-  double2* ring = reinterpret_cast<double2*>(hbsm) + (size_t)warp * DEPTH * rs;
+  double2* ring = reinterpret_cast<double2*>(hbsm) + (size_t)warp * (HBK::DEPTH0 * n32 + 32);
   const double2 zero = make_double2(0.0, 0.0);
-  const int nblk = (n + 31) / 32;
 
   double2 x[NPL];
 #pragma unroll
@@ -412,31 +439,42 @@ __global__ void __launch_bounds__(HessBig<NPL>::THREADS) hess_solve_big_kernel(H
     for (int e = 0; e < NPL; ++e)
       if (e == b) x[e] = v;
   };
-  // ---- forward: (R^H) w = q.  After w_j is final, row j of R updates the entries k > j. ----
-  auto fetch_row = [&](int j) {  // entries k > j of row j (+ rinv[j]) -> ring slot j % DEPTH (always commits a group)
-    if (j < n) {
-      double2* dst = ring + (size_t)(j % DEPTH) * rs;
-      const int e0 = j >> 5;
-#pragma unroll
-      for (int e = 0; e < NPL; ++e) {
-        const int k = 32 * e + lane;
-        if (e >= e0 && k > j && k < n) cp_async16(dst + k, Rr + (size_t)j * n + k);
-      }
-      if (lane == 0) cp_async16(dst + n32, rinv + j);
-    }
-    cp_async_commit();
+  // level of a phase position with `rem` blocks left to stream: the deepest L with rem <= nblk >> L (and a non-empty cut)
+  auto level_of = [&](int rem) {
+    int L = 0;
+    while (L + 1 < HBK::LEVELS && (nblk >> (L + 1)) >= 1 && rem <= (nblk >> (L + 1))) ++L;
+    return L;
   };
+
+  // ---- forward: (R^H) w = q.  After w_j is final, row j of R updates the entries k > j. ----
+  // One pivot block (32 rows) at ring geometry (DEPTH rows of `rs` elements; element k of a row at index k - 32 * kb).
+  auto fwd_block = [&](auto depth_tag, int je, int rs, int kb, bool prime) {
+    constexpr int DEPTH = decltype(depth_tag)::value;
+    auto fetch_row = [&](int j) {  // entries k > j of row j (+ rinv[j]) -> ring slot j % DEPTH (always commits a group)
+      if (j < n) {
+        double2* dst = ring + (size_t)(j % DEPTH) * rs;
+        const int e0 = j >> 5;
 #pragma unroll
-  for (int d = 0; d < DEPTH; ++d) fetch_row(d);
-  for (int je = 0; je < nblk; ++je) {
+        for (int e = 0; e < NPL; ++e) {
+          const int k = 32 * e + lane;
+          if (e >= e0 && k > j && k < n) cp_async16(dst + (k - 32 * kb), Rr + (size_t)j * n + k);
+        }
+        if (lane == 0) cp_async16(dst + rs - 1, rinv + j);
+      }
+      cp_async_commit();
+    };
+    if (prime) {
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d) fetch_row(32 * je + d);
+    }
     double2 xe = get_block(je);
     const int jend = min(32, n - 32 * je);
     for (int jl = 0; jl < jend; ++jl) {
       const int j = 32 * je + jl;
       cp_async_wait<DEPTH - 1>();
       __syncwarp();
-      const double2* row = ring + (size_t)(j % DEPTH) * rs;
-      const double2 rj = row[n32];
+      const double2* row = ring + (size_t)(j % DEPTH) * rs - 32 * kb;
+      const double2 rj = row[32 * kb + rs - 1];
       const double xr = __shfl_sync(0xffffffffu, xe.x, jl), xi = __shfl_sync(0xffffffffu, xe.y, jl);
       const double2 wj = cmul(make_double2(xr, xi), make_double2(rj.x, -rj.y));  // / conj(R[j,j])
       if (lane == jl) xe = wj;
@@ -460,33 +498,57 @@ __global__ void __launch_bounds__(HessBig<NPL>::THREADS) hess_solve_big_kernel(H
       fetch_row(j + DEPTH);
     }
     put_block(je, xe);
+  };
+  {
+    int cur = -1;
+    for (int je = 0; je < nblk; ++je) {
+      const int L = level_of(nblk - je);
+      const bool prime = L != cur;
+      if (prime && cur >= 0) {  // re-cut the ring: everything in flight belongs to the old geometry
+        cp_async_wait<0>();
+        __syncwarp();
+      }
+      cur = L;
+      const int blocks = L == 0 ? nblk : (nblk >> L);  // blocks a row of this level can span
+      const int rs = 32 * blocks + 1, kb = nblk - blocks;
+      switch (L) {
+        case 0: fwd_block(std::integral_constant<int, HBK::DEPTH0>{}, je, rs, kb, prime); break;
+        case 1: fwd_block(std::integral_constant<int, 2 * HBK::DEPTH0>{}, je, rs, kb, prime); break;
+        case 2: fwd_block(std::integral_constant<int, 4 * HBK::DEPTH0>{}, je, rs, kb, prime); break;
+        default: fwd_block(std::integral_constant<int, 8 * HBK::DEPTH0>{}, je, rs, kb, prime); break;
+      }
+    }
   }
   cp_async_wait<0>();
   __syncwarp();
   // ---- backward: R v = w.  After v_k is final, column k of R updates the entries i < k. ----
-  auto fetch_col = [&](int k) {  // entries i < k of column k (+ rinv[k]) -> ring slot k % DEPTH
-    if (k >= 0) {
-      double2* dst = ring + (size_t)(k % DEPTH) * rs;
-      const int e1 = k >> 5;
+  auto bwd_block = [&](auto depth_tag, int ke, int rs, bool prime) {
+    constexpr int DEPTH = decltype(depth_tag)::value;
+    auto fetch_col = [&](int k) {  // entries i < k of column k (+ rinv[k]) -> ring slot k % DEPTH
+      if (k >= 0) {
+        double2* dst = ring + (size_t)(k % DEPTH) * rs;
+        const int e1 = k >> 5;
 #pragma unroll
-      for (int e = 0; e < NPL; ++e) {
-        const int i = 32 * e + lane;
-        if (e <= e1 && i < k) cp_async16(dst + i, Rc + (size_t)k * n + i);
+        for (int e = 0; e < NPL; ++e) {
+          const int i = 32 * e + lane;
+          if (e <= e1 && i < k) cp_async16(dst + i, Rc + (size_t)k * n + i);
+        }
+        if (lane == 0) cp_async16(dst + rs - 1, rinv + k);
       }
-      if (lane == 0) cp_async16(dst + n32, rinv + k);
-    }
-    cp_async_commit();
-  };
+      cp_async_commit();
+    };
+    const int ktop = min(32 * ke + 31, n - 1);
+    if (prime) {
 #pragma unroll
-  for (int d = 0; d < DEPTH; ++d) fetch_col(n - 1 - d);
-  for (int ke = nblk - 1; ke >= 0; --ke) {
+      for (int d = 0; d < DEPTH; ++d) fetch_col(ktop - d);
+    }
     double2 xe = get_block(ke);
-    for (int kl = min(31, n - 1 - 32 * ke); kl >= 0; --kl) {
-      const int k = 32 * ke + kl;
+    for (int k = ktop; k >= 32 * ke; --k) {
+      const int kl = k & 31;
       cp_async_wait<DEPTH - 1>();
       __syncwarp();
       const double2* col = ring + (size_t)(k % DEPTH) * rs;
-      const double2 rk = col[n32];
+      const double2 rk = col[rs - 1];
       const double xr = __shfl_sync(0xffffffffu, xe.x, kl), xi = __shfl_sync(0xffffffffu, xe.y, kl);
       const double2 vk = cmul(make_double2(xr, xi), rk);
       if (lane == kl) xe = vk;
@@ -498,6 +560,26 @@ __global__ void __launch_bounds__(HessBig<NPL>::THREADS) hess_solve_big_kernel(H
       fetch_col(k - DEPTH);
     }
     put_block(ke, xe);
+  };
+  {
+    int cur = -1;
+    for (int ke = nblk - 1; ke >= 0; --ke) {
+      const int L = level_of(ke + 1);
+      const bool prime = L != cur;
+      if (prime && cur >= 0) {
+        cp_async_wait<0>();
+        __syncwarp();
+      }
+      cur = L;
+      const int blocks = L == 0 ? nblk : (nblk >> L);
+      const int rs = 32 * blocks + 1;
+      switch (L) {
+        case 0: bwd_block(std::integral_constant<int, HBK::DEPTH0>{}, ke, rs, prime); break;
+        case 1: bwd_block(std::integral_constant<int, 2 * HBK::DEPTH0>{}, ke, rs, prime); break;
+        case 2: bwd_block(std::integral_constant<int, 4 * HBK::DEPTH0>{}, ke, rs, prime); break;
+        default: bwd_block(std::integral_constant<int, 8 * HBK::DEPTH0>{}, ke, rs, prime); break;
+      }
+    }
   }
   cp_async_wait<0>();
   double2* out = P.Wv + (size_t)slot * P.n_pad;

@@ -136,17 +136,19 @@ def test_hessqr_arnoldi_projection_vs_oracle(gpu):
     assert algo == "HessQR" and _rel(Z, Zc, _floor(H)) < RTOL and np.mean(it == itc) > 0.97
 
 
-@pytest.mark.parametrize("n", [300, 600])
+@pytest.mark.parametrize("n", [300, 600, 1000])
 def test_hessqr_large_n_streaming_kernels(gpu, n, monkeypatch):
     """256 < n <= 1024: warp-per-slot streaming kernel with 16 / 32 vector elements per lane (hess_solve_big_kernel);
     PSA_HESS_CTA=1 selects the CTA-per-slot kernel (different summation order: agreement to rounding, not bit for bit)."""
     rng = np.random.default_rng(11)
-    H = np.triu(rng.standard_normal((n + 1, n)) + 1j * rng.standard_normal((n + 1, n)), -1)
-    x, y = np.linspace(-3, 3, 5), np.linspace(-3, 3, 4)
+    H = np.triu(rng.standard_normal((n + 1, n)) + 1j * rng.standard_normal((n + 1, n)), -1) / np.sqrt(n)
+    H[np.arange(1, n + 1), np.arange(n)] = 1.0           # spectrum of the square part ~ unit disc: the window sees real sigma_min
+    x, y = np.linspace(-1.5, 1.5, 5), np.linspace(-1.5, 1.5, 4)
     q0 = po.start_vector(n, 1)
-    gpu.set_matrix(H)
+    gpu.set_matrix(np.asfortranarray(H))
     Z, it, counts, algo = gpu.grid(x, y, q0)
     Zc, itc, _ = co.grid(H, x, y, q0, nthreads=8)
+    assert np.sum(Zc > _floor(H)) >= 10
     assert algo == "HessQR" and _rel(Z, Zc, _floor(H)) < RTOL and np.mean(it == itc) > 0.9
     monkeypatch.setenv("PSA_HESS_CTA", "1")
     Z2, it2, _, _ = gpu.grid(x, y, q0)
