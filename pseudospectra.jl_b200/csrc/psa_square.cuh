@@ -728,7 +728,7 @@ __device__ __forceinline__ void solve_deep_body(const SolveParams& P) {
     unsigned char* sb = smem + stage * STAGE_BYTES;
     const int flip = cons.phase ? (KC - 1) : 0;
     if constexpr (LANE_SOLVE) wm = (wq + cons.I + pi) & 3;  // ownership rotates: every warp solves one chunk per block row
-    if constexpr (LANE_SOLVE) {
+    {
       // A run of GEMM steps (the rest of this block row's off-diagonal tiles) in a tight loop: the ring position advances
       // by increments, nothing else is recomputed per step.  No __syncwarp before the release: mma.sync is a warp-wide
       // instruction, so once the step's last DMMA has issued every lane's fragment loads from the stage have completed.
