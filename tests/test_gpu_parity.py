@@ -136,7 +136,7 @@ def test_hessqr_arnoldi_projection_vs_oracle(gpu):
     assert algo == "HessQR" and _rel(Z, Zc, _floor(H)) < RTOL and np.mean(it == itc) > 0.97
 
 
-@pytest.mark.parametrize("n", [300, 600, 1000])
+@pytest.mark.parametrize("n", [257, 300, 600, 1000, 1024])
 def test_hessqr_large_n_streaming_kernels(gpu, n, monkeypatch):
     """256 < n <= 1024: warp-per-slot streaming kernel with 16 / 32 vector elements per lane (hess_solve_big_kernel);
     PSA_HESS_CTA=1 selects the CTA-per-slot kernel (different summation order: agreement to rounding, not bit for bit)."""
