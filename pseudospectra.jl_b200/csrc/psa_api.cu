@@ -24,6 +24,7 @@
 #include "psa_project.cuh"
 #include "psa_square.cuh"
 #include "psa_cluster.cuh"
+#include "psa_point.cuh"
 #include "psa_svd.cuh"
 
 namespace {
@@ -84,10 +85,14 @@ struct Device {
   double2* slot_z = nullptr;
   double *slot_beta = nullptr, *slot_sigold = nullptr, *hist_alpha = nullptr, *hist_beta = nullptr;
   int *active = nullptr, *fresh = nullptr, *state = nullptr;
-  unsigned long long* host_state = nullptr;      // pinned + mapped: [0] (tick << 32) | n_active, [1] (tick << 32) | n_fresh
+  unsigned long long* host_state = nullptr;      // pinned + mapped: [0] (tick << 32) | n_active, [1] (tick << 32) | n_fresh,
+                                                 // [2] stop word of the point-resident kernel (cancel flag)
   unsigned long long* host_state_dev = nullptr;  // device alias
   unsigned long long* counts = nullptr;
   unsigned long long* scratch64 = nullptr;  // 4 words: structure-check counter, post-processing reductions
+  // point-resident Lanczos kernel (small n): per-warp alpha / beta histories
+  double* pt_hist = nullptr;
+  size_t pt_hist_cap = 0;
   // HessQR workspace
   double2* R = nullptr;  // per-slot triangular factors
   size_t R_elems = 0;
@@ -201,7 +206,7 @@ void free_device(Device& d) {
   free_slots(d);
   void* ptrs[] = {d.key_static, d.prog, d.diagT, d.key_in, d.key_out, d.ord_in, d.ord_out, d.sort_tmp, d.T,     d.packA, d.packB,
                   d.state, d.counts, d.scratch64, d.x,    d.y,       d.Z,        d.q0,    d.row_batch, d.iters,
-                  d.Zfull, d.itfull, d.post,      d.basis, d.yvec, d.Tp, d.Twork, d.proj_sel, d.proj_start, d.proj_rot};
+                  d.Zfull, d.itfull, d.post,      d.basis, d.yvec, d.Tp, d.Twork, d.proj_sel, d.proj_start, d.proj_rot, d.pt_hist};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (d.host_state) cudaFreeHost(d.host_state);
@@ -309,6 +314,7 @@ int set_solve_attr(Context* ctx) {
                                         2 * HIST_MAX * (int)sizeof(double)) != cudaSuccess)
       rc = -1;
     if (rc == 0) rc = hess_set_attrs();
+    if (rc == 0) rc = point_set_attrs();
     if (rc == 0 && cudaFuncSetAttribute(svd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) rc = -1;
     if (rc != 0) {
       ctx->err = "cudaFuncSetAttribute failed";
@@ -428,6 +434,9 @@ int run_grid(Context* ctx, const GridArgs& g, const std::vector<const int*>& row
   if (rc) return rc;
   if (g.maxit > HIST_MAX - 2) return PSA_ERR_ARG;
   const int hist = std::max(HIST_MIN, (g.maxit + 2 + 31) / 32 * 32);
+  // small square matrices: one persistent launch, a warp per grid point (psa_point.cuh); shape-only decision
+  const int pt_w = ctx->algo == PSA_ALGO_SQ_LANC && !getenv("PSA_NO_POINT_KERNEL") ? pt_warps(ctx->n, hist) : 0;
+  const bool point_mode = pt_w > 0;
   std::vector<int> rows(ng), P(ng);
   std::vector<const int*> order(ng, nullptr);
   std::vector<TickState> ts(ng);
@@ -439,7 +448,7 @@ int run_grid(Context* ctx, const GridArgs& g, const std::vector<const int*>& row
     rows[i] = (g.ly - i + ng - 1) / ng;
     P[i] = rows[i] * g.lx;
     PSA_CUDA(cudaSetDevice(d.dev));
-    if (ctx->algo != PSA_ALGO_SVD) {  // the SVD branch has no Lanczos state
+    if (ctx->algo != PSA_ALGO_SVD && !point_mode) {  // the SVD branch has no Lanczos state, the point kernel keeps it in registers
       if ((rc = ensure_slots(ctx, d, slot_capacity(ctx, d, P[i]), hist))) return rc;
       PSA_CUDA(cudaMemsetAsync(d.slot_point, 0xff, (d.W + 1) * sizeof(int), d.stream));
     }
@@ -447,9 +456,11 @@ int run_grid(Context* ctx, const GridArgs& g, const std::vector<const int*>& row
     PSA_CUDA(cudaMemsetAsync(d.counts, 0, PSA_NCOUNTS * sizeof(unsigned long long), d.stream));
     d.host_state[0] = 0;
     d.host_state[1] = 0;
+    d.host_state[2] = 0;
     PSA_CUDA(cudaEventRecord(d.g0, d.stream));
     if (P[i] == 0) ts[i].done = true;
-    if (ctx->algo == PSA_ALGO_SQ_LANC && P[i] > d.W && !getenv("PSA_NATURAL_ORDER")) {
+    const long long in_flight = point_mode ? (long long)d.num_sms * pt_w : (long long)d.W;
+    if (ctx->algo == PSA_ALGO_SQ_LANC && P[i] > in_flight && !getenv("PSA_NATURAL_ORDER")) {
       // more points than slots: queue them longest-job-first (see predict_kernel)
       if (d.ord_cap < (size_t)P[i]) {
         d.ord_cap = 0;
@@ -462,7 +473,7 @@ int run_grid(Context* ctx, const GridArgs& g, const std::vector<const int*>& row
         d.ord_cap = (size_t)P[i];
       }
       // dynamic queue order (see rekey_kernel): only worth its two small launches per tick when ticks are heavy
-      const bool dynamic = !getenv("PSA_STATIC_ORDER") && 8.0 * ctx->n * (double)ctx->n * d.W / 2.5e10 >= 3.0;
+      const bool dynamic = !point_mode && !getenv("PSA_STATIC_ORDER") && 8.0 * ctx->n * (double)ctx->n * d.W / 2.5e10 >= 3.0;
       if (dynamic) {
         dyn_stride[i] = std::max(1, (int)std::sqrt((double)P[i] / (0.5 * d.W)));
         PSA_CUDA(cudaMemsetAsync(d.prog, 0, (size_t)P[i] * sizeof(int), d.stream));
@@ -519,6 +530,70 @@ int run_grid(Context* ctx, const GridArgs& g, const std::vector<const int*>& row
       PSA_CUDA(cudaGetLastError());
       launches += 1;
       ts[i].done = true;
+    }
+  }
+
+  bool cancelled = false;
+  if (point_mode) {
+    // one launch per device over all of its points; warps pull points from an atomic queue
+    if (g.cancel && *g.cancel == 1) cancelled = true;
+    for (int i = 0; i < ng; ++i) ts[i].done = true;
+    for (int i = 0; i < ng && !cancelled; ++i) {
+      Device& d = ctx->devs[i];
+      PSA_CUDA(cudaSetDevice(d.dev));
+      if (P[i] == 0) continue;
+      const int ctas = std::min(d.num_sms, (P[i] + pt_w - 1) / pt_w);
+      const size_t pt_slots = (size_t)ctas * pt_w;  // per warp: alpha and beta histories, then the previous Lanczos vector
+      if ((rc = ensure_cap(ctx, &d.pt_hist, &d.pt_hist_cap, pt_slots * (2 * (size_t)hist + 2 * PT_MAX_NPL * 32)))) return rc;
+      PointParams pp;
+      pp.n = ctx->n;
+      pp.T = d.Tcur;
+      pp.ldt = ctx->m;
+      pp.P = P[i];
+      pp.rows_local = rows[i];
+      pp.row0 = i;
+      pp.row_step = ng;
+      pp.x = d.x;
+      pp.y = d.y;
+      pp.order = order[i];
+      pp.row_batch = row_batch[i];
+      pp.q0 = d.q0;
+      pp.n_pad = ctx->n_pad;
+      pp.tol = g.tol;
+      pp.maxit = g.maxit;
+      pp.bigsigma = g.bigsigma;
+      pp.Z = Zout[i];
+      pp.iters = itout[i];
+      pp.counts = d.counts;
+      pp.queue = d.state + 6;
+      pp.stop = g.cancel ? d.host_state_dev + 2 : nullptr;
+      pp.hist_alpha = d.pt_hist;
+      pp.hist_beta = d.pt_hist + pt_slots * hist;
+      pp.qold = reinterpret_cast<double2*>(d.pt_hist + 2 * pt_slots * hist);
+      pp.hist = hist;
+      EventPair& ep = event_pair(d, ts[i].nev++);
+      PSA_CUDA(cudaEventRecord(ep.a, d.stream));
+      launch_point_lanczos(pp, ctas, pt_w, d.stream);
+      PSA_CUDA(cudaEventRecord(ep.b, d.stream));
+      PSA_CUDA(cudaGetLastError());
+      launches += 1;
+    }
+    // the cancel flag (compute.jl:202-204) is forwarded to the running kernels through the mapped stop word
+    unsigned idle_pt = 0;
+    while (g.cancel && !cancelled) {
+      bool busy = false;
+      for (int i = 0; i < ng; ++i) {
+        PSA_CUDA(cudaSetDevice(ctx->devs[i].dev));
+        const cudaError_t qe = cudaStreamQuery(ctx->devs[i].stream);
+        if (qe == cudaErrorNotReady) busy = true;
+        else if (qe != cudaSuccess) PSA_CUDA(qe);
+      }
+      if (!busy) break;
+      if (*g.cancel == 1) {
+        for (int i = 0; i < ng; ++i) *(volatile unsigned long long*)&ctx->devs[i].host_state[2] = 1ull;
+        cancelled = true;
+      }
+      short_pause(idle_pt);
     }
   }
 
@@ -648,7 +723,6 @@ int run_grid(Context* ctx, const GridArgs& g, const std::vector<const int*>& row
 
   int remaining = 0;
   for (int i = 0; i < ng; ++i) remaining += !ts[i].done;
-  bool cancelled = false;
   unsigned idle = 0;
   while (remaining > 0) {
     if (g.cancel && *g.cancel == 1) {
@@ -703,7 +777,7 @@ int run_grid(Context* ctx, const GridArgs& g, const std::vector<const int*>& row
     cudaEventElapsedTime(&gms, d.g0, d.g1);
     max_ms = std::max(max_ms, (double)gms);
     if (i == 0) {
-      const size_t live = ctx->algo == PSA_ALGO_SVD ? ts[i].nev : std::min<size_t>(ts[i].nev, (size_t)st[3]);
+      const size_t live = (ctx->algo == PSA_ALGO_SVD || point_mode) ? ts[i].nev : std::min<size_t>(ts[i].nev, (size_t)st[3]);
       double solve_ms = 0;
       for (size_t e = 0; e < live; ++e) {  // groups launched past the last live tick are empty: not counted
         float ms = 0;
@@ -967,7 +1041,7 @@ int psa_gpu_init(int ngpus, const int* device_ids, void** out) {
     ok = ok && cudaMalloc((void**)&d.state, 8 * sizeof(int)) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&d.counts, PSA_NCOUNTS * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&d.scratch64, 4 * sizeof(unsigned long long)) == cudaSuccess;
-    ok = ok && cudaHostAlloc((void**)&d.host_state, 2 * sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess;
+    ok = ok && cudaHostAlloc((void**)&d.host_state, 4 * sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess;
     ok = ok && cudaHostGetDevicePointer((void**)&d.host_state_dev, d.host_state, 0) == cudaSuccess;
     ok = ok && cudaEventCreate(&d.g0) == cudaSuccess && cudaEventCreate(&d.g1) == cudaSuccess;
     if (!ok) {

@@ -733,3 +733,52 @@ def test_kernel_variants_are_bit_identical(gpu, monkeypatch):
         assert np.array_equal(gpu.apply_resolvent(z, Q), V0), (width, "multi")
         monkeypatch.delenv("PSA_MULTI")
         monkeypatch.delenv("PSA_DEEP_CW")
+
+
+@pytest.mark.parametrize("n", [55, 64, 97, 150, 163])
+def test_point_resident_kernel_small_matrices(gpu, n, monkeypatch):
+    """Small square matrices run `_psa_lanczos!` (compute.jl:619-665) one warp per grid point in a single launch
+    (csrc/psa_point.cuh) instead of ticks of the DMMA kernels.  Same contract: sigma_min within 1e-6 of the oracle,
+    iteration counts equal, the same points non-converged -- and the tick engine (PSA_NO_POINT_KERNEL=1) agrees.
+    n covers the register-block boundaries of the kernel and the largest size that fits beside the matrix."""
+    T, eigA = po.complex_schur(po.random_complex(n, n))
+    q0 = po.start_vector(n, 1)
+    ax = po.vec2ax(eigA)
+    x, y = np.linspace(ax[0], ax[1], 23), np.linspace(ax[2], ax[3], 19)
+    gpu.set_matrix(T)
+    Z, it, counts, algo = gpu.grid(x, y, q0)
+    st = gpu.last_stats()
+    assert algo == "sq_lanc" and st["ticks"] == 0 and st["total_launches"] <= 4  # one kernel (+ queue-order launches)
+    Zc, itc, flc = co.grid(T, x, y, q0, nthreads=8)
+    assert _rel(Z, Zc, _floor(T)) < RTOL and np.mean(it == itc) >= 0.995
+    assert counts[3] == Z.size and counts[2] == it.sum() and counts[0] == (flc & 1).sum()
+    monkeypatch.setenv("PSA_NO_POINT_KERNEL", "1")
+    Zt, itt, ct, _ = gpu.grid(x, y, q0)
+    assert gpu.last_stats()["ticks"] > 0
+    assert _rel(Z, Zt, _floor(T)) < 1e-9 and np.mean(it == itt) >= 0.995
+    monkeypatch.delenv("PSA_NO_POINT_KERNEL")
+    Z3, it3, c3, _ = gpu.grid(x, y, q0, maxit=3)  # non-convergence is counted (compute.jl:603-606)
+    Zc3, itc3, flc3 = co.grid(T, x, y, q0, maxit=3, nthreads=8)
+    assert it3.max() <= 3 and c3[0] == (flc3 & 1).sum() and _rel(Z3, Zc3, _floor(T)) < RTOL
+    Zl, _, _, _ = gpu.grid(x, y, q0, maxit=2000)  # long histories do not fit beside the matrix: tick engine, same answer
+    assert gpu.last_stats()["ticks"] > 0 and _rel(Zl, Z, _floor(T)) < 1e-9
+
+
+def test_point_resident_kernel_batched_start_vectors_and_order(pkg, gpu):
+    """Per-batch start vectors (compute.jl:199-208) and more points than warps in flight (queue order) through the
+    point kernel: equal to the oracle run batch by batch; a second call returns the same bits (no scheduling effects)."""
+    n = 120
+    T, eigA = po.complex_schur(po.random_complex(n, 9))
+    ax = po.vec2ax(eigA)
+    x, y = np.linspace(ax[0], ax[1], 70), np.linspace(ax[2], ax[3], 64)  # 4480 points > 148 x 16 warps
+    rb = (np.arange(len(y)) // 20).astype(np.int32)
+    qs = np.stack([po.start_vector(n, s) for s in range(rb.max() + 1)])
+    gpu.set_matrix(T)
+    Z, it, counts, algo = gpu.grid(x, y, qs, row_batch=rb)
+    assert gpu.last_stats()["ticks"] == 0
+    for b in range(rb.max() + 1):
+        rows = np.flatnonzero(rb == b)[::5]
+        Zc, itc, _ = co.grid(T, x, y[rows], qs[b], nthreads=8)
+        assert _rel(Z[rows], Zc, _floor(T)) < RTOL and np.mean(it[rows] == itc) >= 0.995
+    Z2, it2, _, _ = gpu.grid(x, y, qs, row_batch=rb)
+    assert np.array_equal(Z, Z2) and np.array_equal(it, it2)
