@@ -56,14 +56,24 @@ struct PointParams {
 };
 
 __host__ __device__ inline size_t pt_tri_elems(int n) { return (size_t)n * (n + 1) / 2; }
-inline size_t pt_smem(int n, int hist, int warps) { return pt_tri_elems(n) * sizeof(double2) + (size_t)warps * 2 * hist * sizeof(double); }
+// shared memory: the packed triangle, ONE zero element (what masked lanes read), then per warp 2 x hist doubles
+__host__ __device__ inline size_t pt_mat_elems(int n) { return pt_tri_elems(n) + 1; }
+inline size_t pt_smem(int n, int hist, int warps) { return pt_mat_elems(n) * sizeof(double2) + (size_t)warps * 2 * hist * sizeof(double); }
 // warps per CTA that fit beside the matrix; 0 = this shape stays on the tick engine
 inline int pt_warps(int n, int hist) {
   if ((n + 31) / 32 > PT_MAX_NPL) return 0;
-  const long long left = (long long)PT_SMEM_BUDGET - (long long)(pt_tri_elems(n) * sizeof(double2));
+  const long long left = (long long)PT_SMEM_BUDGET - (long long)(pt_mat_elems(n) * sizeof(double2));
   const long long w = left / (2LL * hist * (long long)sizeof(double));
   if (w < PT_MIN_WARPS) return 0;
   return (int)(w < PT_MAX_WARPS ? w : PT_MAX_WARPS);
+}
+
+// 16-byte shared-memory load by shared-window address (the matrix is read-only after staging: no memory clobber, the
+// compiler is free to schedule these loads ahead of the dependent chain)
+__device__ __forceinline__ double2 pt_lds(uint32_t addr) {
+  double2 v;
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
 }
 
 template <int NPL>
@@ -72,7 +82,7 @@ __global__ void __launch_bounds__(PT_MAX_WARPS * 32, 1) point_lanczos_kernel(Poi
   double2* Ts = reinterpret_cast<double2*>(pt_smem_raw);
   const int n = S.n;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  double* sd = reinterpret_cast<double*>(pt_smem_raw + pt_tri_elems(n) * sizeof(double2)) + (size_t)wid * 2 * S.hist;
+  double* sd = reinterpret_cast<double*>(pt_smem_raw + pt_mat_elems(n) * sizeof(double2)) + (size_t)wid * 2 * S.hist;
   double* se2 = sd + S.hist;
   double* ha = S.hist_alpha + ((size_t)blockIdx.x * nw + wid) * S.hist;
   double* hb = S.hist_beta + ((size_t)blockIdx.x * nw + wid) * S.hist;
@@ -85,14 +95,14 @@ __global__ void __launch_bounds__(PT_MAX_WARPS * 32, 1) point_lanczos_kernel(Poi
     double2* dst = Ts + (size_t)j * (j + 1) / 2;
     for (int i = lane; i <= j; i += 32) dst[i] = col[i];
   }
+  const int zero_idx = (int)pt_tri_elems(n);
+  if (threadIdx.x == 0) Ts[zero_idx] = make_double2(0.0, 0.0);
   __syncthreads();
 
-  int tri[NPL];  // i (i + 1) / 2 for this lane's elements
-#pragma unroll
-  for (int r = 0; r < NPL; ++r) {
-    const int i = r * 32 + lane;
-    tri[r] = i * (i + 1) / 2;
-  }
+  // Shared-window byte addresses.  Row j of T as this lane sees it: element (j, i), i = 32 r + lane, sits at
+  // row0[r] + 16 j.  Lanes beyond the matrix (i >= n) and masked lanes read the zero element instead, so their vector
+  // entries stay exactly 0 without any select on the FP64 side.
+  const uint32_t ts0 = smem_u32(Ts), zaddr = ts0 + 16u * (uint32_t)zero_idx;
 
   for (;;) {
     int qpos = 0;
@@ -119,7 +129,7 @@ __global__ void __launch_bounds__(PT_MAX_WARPS * 32, 1) point_lanczos_kernel(Poi
       const int i = r * 32 + lane;
       double2 d = make_double2(1.0, 0.0);
       if (i < n) {
-        d = Ts[tri[r] + i];
+        d = Ts[i * (i + 1) / 2 + i];
         d.x -= zx;
         d.y -= zy;
       }
@@ -133,32 +143,37 @@ __global__ void __launch_bounds__(PT_MAX_WARPS * 32, 1) point_lanczos_kernel(Poi
 #pragma unroll
       for (int r = 0; r < NPL; ++r) b[r] = q[r];
 
-      // w = F1' \ q : forward sweep over the columns of L = F1^H, L[i][j] = conj(T[j][i]) (i > j), pivot conj(t_jj - z)
+      // w = F1' \ q : forward sweep over the columns of L = F1^H, L[i][j] = conj(T[j][i]) (i > j), pivot conj(t_jj - z).
+      // Within the diagonal register block an entry is final once its own column has been processed (later columns
+      // are masked for it), so the pivot scaling of the stored entries is applied once per block, after its columns.
 #pragma unroll
       for (int r = 0; r < NPL; ++r) {
         const int j0 = r * 32;
         const int cnt = min(32, n - j0);
         const double2 rdr = pivot_inv(r);
         const double2 rdc = make_double2(rdr.x, -rdr.y);
+        uint32_t row[NPL], rstep[NPL];  // address of element (j, i) for the current column j, and its step per column
+#pragma unroll
+        for (int rr = r; rr < NPL; ++rr) {
+          const int i = rr * 32 + lane;
+          row[rr] = i < n ? ts0 + 16u * (uint32_t)(i * (i + 1) / 2 + j0) : zaddr;
+          rstep[rr] = i < n ? 16u : 0u;
+        }
         for (int ll = 0; ll < cnt; ++ll) {
-          const int j = j0 + ll;
-          const double2 c = cmul(b[r], rdc);
+          const double2 c = cmul_fixed(b[r], rdc);
           const double wx = __shfl_sync(FULL, c.x, ll), wy = __shfl_sync(FULL, c.y, ll);
-          if (lane == ll) b[r] = c;
+          const double nwx = -wx, nwy = -wy;
 #pragma unroll
           for (int rr = r; rr < NPL; ++rr) {
-            // branch-free: lanes that own no element i > j of this register block read element 0 and use t = 0
-            const int i = rr * 32 + lane;
-            const bool act = (rr == r) ? (lane > ll && i < n) : (i < n);
-            double2 t = Ts[act ? tri[rr] + j : 0];  // T[j][i]
-            t.x = act ? t.x : 0.0;
-            t.y = act ? t.y : 0.0;
-            b[rr].x = fma(-t.x, wx, b[rr].x);  // b_i -= conj(t) * w_j
-            b[rr].x = fma(-t.y, wy, b[rr].x);
-            b[rr].y = fma(-t.x, wy, b[rr].y);
+            const double2 t = pt_lds((rr == r && lane <= ll) ? zaddr : row[rr]);  // T[j][i]; only i > j is updated
+            row[rr] += rstep[rr];
+            b[rr].x = fma(t.x, nwx, b[rr].x);  // b_i -= conj(t) * w_j
+            b[rr].x = fma(t.y, nwy, b[rr].x);
+            b[rr].y = fma(t.x, nwy, b[rr].y);
             b[rr].y = fma(t.y, wx, b[rr].y);
           }
         }
+        b[r] = cmul_fixed(b[r], rdc);
       }
       // v = F1 \ w : backward sweep over the columns of T
 #pragma unroll
@@ -166,21 +181,23 @@ __global__ void __launch_bounds__(PT_MAX_WARPS * 32, 1) point_lanczos_kernel(Poi
         const int j0 = r * 32;
         const int cnt = min(32, n - j0);
         const double2 rdr = pivot_inv(r);
-        for (int ll = cnt - 1; ll >= 0; --ll) {
-          const int j = j0 + ll;
-          const double2 c = cmul(b[r], rdr);
-          const double2 v = make_double2(__shfl_sync(FULL, c.x, ll), __shfl_sync(FULL, c.y, ll));
-          if (lane == ll) b[r] = c;
-          const double2* colj = Ts + j * (j + 1) / 2;
+        int j = j0 + cnt - 1;
+        uint32_t col = ts0 + 16u * (uint32_t)(j * (j + 1) / 2 + lane);  // address of element (lane, j)
+        for (int ll = cnt - 1; ll >= 0; --ll, --j) {
+          const double2 c = cmul_fixed(b[r], rdr);
+          const double vx = __shfl_sync(FULL, c.x, ll), vy = __shfl_sync(FULL, c.y, ll);
+          const double nvx = -vx, nvy = -vy;
 #pragma unroll
           for (int rr = 0; rr <= r; ++rr) {
-            const bool act = (rr == r) ? (lane < ll) : true;
-            double2 t = colj[act ? rr * 32 + lane : 0];  // T[i][j], i < j
-            t.x = act ? t.x : 0.0;
-            t.y = act ? t.y : 0.0;
-            cmsub(b[rr], t, v);  // b_i -= T[i][j] * v_j
+            const double2 t = pt_lds((rr == r && lane >= ll) ? zaddr : col + 512u * rr);  // T[i][j]; only i < j is updated
+            b[rr].x = fma(t.x, nvx, b[rr].x);  // b_i -= t * v_j
+            b[rr].x = fma(t.y, vy, b[rr].x);
+            b[rr].y = fma(t.x, nvy, b[rr].y);
+            b[rr].y = fma(t.y, nvx, b[rr].y);
           }
+          col -= 16u * (uint32_t)j;  // column j - 1 starts j elements earlier
         }
+        b[r] = cmul_fixed(b[r], rdr);
       }
 
       // v -= beta * qold ; alpha = Re(q . v)          (compute.jl:630-631; same order as lanczos_warp_kernel)

@@ -85,3 +85,25 @@ def test_multi_device_projection(pkg):
             res.append(out)
     assert res[0][5].shape == res[1][5].shape and 55 <= res[0][5].shape[0] < 260
     assert np.array_equal(res[0][5], res[1][5]) and np.array_equal(res[0][0], res[1][0])
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("ly,lx", [(3, 5), (90, 64)])
+def test_multi_device_point_resident_kernel(pkg, ly, lx):
+    """Small matrices (n <= 163) run the point-resident kernel (csrc/psa_point.cuh) on every device: one launch per
+    device over its rows, each with its own queue; bitwise equal to one device (a point's arithmetic does not depend on
+    which warp of which device picks it up)."""
+    T, eigA = po.complex_schur(po.readme_matrix(150))
+    ax = po.vec2ax(eigA)
+    x, y = np.linspace(ax[0], ax[1], lx), np.linspace(ax[2], ax[3], ly)
+    q0 = po.start_vector(150, 0)
+    with pkg.PsaGpu(1) as g1:
+        g1.set_matrix(T)
+        Z1, it1, c1, a1 = g1.grid(x, y, q0)
+        assert g1.last_stats()["ticks"] == 0
+    with pkg.PsaGpu(min(_ngpus(), 4)) as g2:
+        g2.set_matrix(T)
+        Z2, it2, c2, a2 = g2.grid(x, y, q0)
+        assert g2.last_stats()["ticks"] == 0
+    assert a1 == a2 == "sq_lanc"
+    assert np.array_equal(Z1, Z2) and np.array_equal(it1, it2) and np.array_equal(c1, c2)
