@@ -53,7 +53,8 @@ extern "C" {
 #define PSA_STAT_SOLVE_LAUNCHES 1
 #define PSA_STAT_TOTAL_LAUNCHES 2 /* all kernels launched by the last grid call */
 #define PSA_STAT_GRID_MS 3       /* device time of the whole grid call, first launch to last */
-#define PSA_STAT_TICKS 4         /* scheduler ticks (one Lanczos iteration of every active shift per tick) */
+#define PSA_STAT_TICKS 4         /* scheduler ticks (one Lanczos iteration of every active shift per tick); 0 when the grid
+                                    ran as ONE launch: the :SVD branch, and sq_lanc with n <= ~163 (point-resident kernel) */
 #define PSA_STAT_FLOPS 5         /* algorithmic real FP64 flops of the last call: 8 n^2 sum(iters) (+ QR for HessQR) */
 #define PSA_STAT_BYTES 6         /* algorithmic bytes for the HBM-bound HessQR path, 0 for sq_lanc */
 #define PSA_STAT_PACK_MS 7       /* device time of the one-time T packing in the last set_matrix */
@@ -107,7 +108,8 @@ int psa_gpu_set_matrix_device(void* ctx, const double* d_T, int64_t ldt, int m, 
  *                          1 <= maxit <= 4094 (PSA_ERR_ARG above: the per-shift alpha/beta history is sized from it)
  *   iters  : nullable, ly x lx int32, Lanczos iterations per point
  *   counts : nullable, PSA_NCOUNTS int64 (see PSA_COUNT_*)
- *   cancel : nullable; polled between scheduler ticks; *cancel == 1 -> PSA_ERR_CANCELLED (compute.jl:202-204)
+ *   cancel : nullable; polled between scheduler ticks (single-launch paths: forwarded to the running kernel, which
+ *            stops fetching grid points); *cancel == 1 -> PSA_ERR_CANCELLED (compute.jl:202-204)
  * Returns the algorithm used (PSA_ALGO_*) through *algo when non-null. */
 int psa_gpu_grid(void* ctx, const double* x, int lx, const double* y, int ly, const double* q0, double tol,
                  int maxit, double bigsigma, double* Z, int32_t* iters, int64_t* counts, int* algo,
