@@ -543,8 +543,8 @@ int run_grid(Context* ctx, const GridArgs& g, const std::vector<const int*>& row
       PSA_CUDA(cudaSetDevice(d.dev));
       if (P[i] == 0) continue;
       const int ctas = std::min(d.num_sms, (P[i] + pt_w - 1) / pt_w);
-      const size_t pt_slots = (size_t)ctas * pt_w;  // per warp: alpha and beta histories, then the previous Lanczos vector
-      if ((rc = ensure_cap(ctx, &d.pt_hist, &d.pt_hist_cap, pt_slots * (2 * (size_t)hist + 2 * PT_MAX_NPL * 32)))) return rc;
+      const size_t pt_slots = (size_t)ctas * pt_w;  // per warp: alpha and beta histories, then the two Lanczos vectors
+      if ((rc = ensure_cap(ctx, &d.pt_hist, &d.pt_hist_cap, pt_slots * (2 * (size_t)hist + 4 * PT_MAX_NPL * 32)))) return rc;
       PointParams pp;
       pp.n = ctx->n;
       pp.T = d.Tcur;

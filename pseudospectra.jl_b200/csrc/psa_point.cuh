@@ -51,7 +51,7 @@ struct PointParams {
   const volatile unsigned long long* stop;  // nullable, mapped host word: non-zero = stop fetching points
   double* hist_alpha;  // [gridDim.x * warps][hist]  unscaled Lanczos coefficients
   double* hist_beta;
-  double2* qold;       // [gridDim.x * warps][PT_MAX_NPL * 32]  previous Lanczos vector (touched once per iteration)
+  double2* qold;       // [gridDim.x * warps][2][PT_MAX_NPL * 32]  q and qold of the warp's point (touched once per iteration)
   int hist;            // stride of the above, and of the per-warp scaled copies in shared memory
 };
 
@@ -86,7 +86,10 @@ __global__ void __launch_bounds__(PT_MAX_WARPS * 32, 1) point_lanczos_kernel(Poi
   double* se2 = sd + S.hist;
   double* ha = S.hist_alpha + ((size_t)blockIdx.x * nw + wid) * S.hist;
   double* hb = S.hist_beta + ((size_t)blockIdx.x * nw + wid) * S.hist;
-  double2* qo = S.qold + ((size_t)blockIdx.x * nw + wid) * (PT_MAX_NPL * 32) + lane;  // element r at qo[32 r]
+  // q and qold live in an L2-resident scratch (two buffers per warp that swap roles every iteration; each lane only ever
+  // touches its own elements: element r at [32 r]): they are needed once per iteration, the registers belong to the sweeps
+  constexpr int VEC = PT_MAX_NPL * 32;
+  double2* const vecs = S.qold + ((size_t)blockIdx.x * nw + wid) * (2 * VEC) + lane;
   constexpr unsigned FULL = 0xffffffffu;
 
   // packed upper triangle: element (i, j), i <= j, at j (j + 1) / 2 + i
@@ -118,11 +121,12 @@ __global__ void __launch_bounds__(PT_MAX_WARPS * 32, 1) point_lanczos_kernel(Poi
     const double zx = S.x[k], zy = S.y[jrow];
     const double2* q0 = S.q0 + (size_t)(S.row_batch ? S.row_batch[jrow] : 0) * S.n_pad;
 
-    double2 q[NPL], b[NPL];
+    double2 b[NPL];
+    int cur = 0;  // buffer that holds q; the other one holds qold
 #pragma unroll
     for (int r = 0; r < NPL; ++r) {
       const int i = r * 32 + lane;
-      q[r] = i < n ? q0[i] : make_double2(0.0, 0.0);  // q = q0[1:n], compute.jl:622
+      __stcg(vecs + 32 * r, i < n ? q0[i] : make_double2(0.0, 0.0));  // q = q0[1:n], compute.jl:622
     }
     // 1 / (t_ii - z) for this lane's element of register block r: diag(T1) = diag(T) - z, compute.jl:595
     auto pivot_inv = [&](int r) {
@@ -140,8 +144,10 @@ __global__ void __launch_bounds__(PT_MAX_WARPS * 32, 1) point_lanczos_kernel(Poi
     int l = 0;
     for (;;) {
       ++l;
+      double2* const qv = vecs + cur * VEC;         // q
+      double2* const qov = vecs + (cur ^ 1) * VEC;  // qold, overwritten by the next q at the end of the iteration
 #pragma unroll
-      for (int r = 0; r < NPL; ++r) b[r] = q[r];
+      for (int r = 0; r < NPL; ++r) b[r] = __ldcg(qv + 32 * r);
 
       // w = F1' \ q : forward sweep over the columns of L = F1^H, L[i][j] = conj(T[j][i]) (i > j), pivot conj(t_jj - z).
       // Within the diagonal register block an entry is final once its own column has been processed (later columns
@@ -202,10 +208,12 @@ __global__ void __launch_bounds__(PT_MAX_WARPS * 32, 1) point_lanczos_kernel(Poi
 
       // v -= beta * qold ; alpha = Re(q . v)          (compute.jl:630-631; same order as lanczos_warp_kernel)
       double part = 0.0;
+      double2 q[NPL];
 #pragma unroll
       for (int r = 0; r < NPL; ++r) {
+        q[r] = __ldcg(qv + 32 * r);
         if (l > 1) {
-          const double2 o = __ldcg(qo + 32 * r);
+          const double2 o = __ldcg(qov + 32 * r);
           b[r].x -= beta * o.x;
           b[r].y -= beta * o.y;
         }
@@ -282,10 +290,9 @@ __global__ void __launch_bounds__(PT_MAX_WARPS * 32, 1) point_lanczos_kernel(Poi
       if (conv || failed || l >= S.maxit) break;
       sigold = sigma;
 #pragma unroll
-      for (int r = 0; r < NPL; ++r) {  // qold = q ; q = v / beta   (compute.jl:634-635)
-        __stcg(qo + 32 * r, q[r]);
-        q[r] = make_double2(b[r].x / beta, b[r].y / beta);
-      }
+      for (int r = 0; r < NPL; ++r)  // qold = q ; q = v / beta   (compute.jl:634-635): the buffers swap roles
+        __stcg(qov + 32 * r, make_double2(b[r].x / beta, b[r].y / beta));
+      cur ^= 1;
     }
     if (lane == 0) {
       S.Z[p] = 1.0 / sqrt(sigma);
