@@ -10,7 +10,7 @@
 // points, so nothing waits for the slowest point:
 //   * the packed upper triangle of T (n(n+1)/2 complex128, 181 KB at n = 150) is staged ONCE per CTA into shared
 //     memory and shared by all of its warps (one CTA per SM, up to 16 warps = 16 points in flight per SM);
-//   * a warp keeps its point's vectors in registers (element i in lane i % 32, register i / 32) and solves in
+//   * a warp keeps the right-hand side of the sweeps in registers (element i in lane i % 32, register i / 32) and solves in
 //     column-sweep (axpy) form: the owner lane of x_j multiplies by the pre-inverted pivot 1 / (t_jj - z), one shuffle
 //     broadcasts it, every lane updates its part of the right-hand side.  The dependent chain per column is
 //     2 FMA + 2 FMA + SHFL; the shared-memory reads are address-independent of it.  Both access patterns are
