@@ -182,6 +182,13 @@ const char* psa_gpu_last_error(void* ctx);
 /* "psagpu <version> sm_100a" */
 const char* psa_gpu_version(void);
 
+/* Which machine a grid call would use for an m x n matrix with the default thresholds of `ComputeThresholds`
+ * (compute.jl:20-27) and the given maxit -- pure host logic, no device needed, nothing is allocated.  Returns the
+ * PSA_ALGO_* branch (PSA_ALGO_NONE: shape not covered) and, through *warps_per_sm when non-null, the number of grid
+ * points one SM keeps in flight in the single-launch point-resident kernel (csrc/psa_point.cuh), or 0 when the shape
+ * runs on the tick engine / the HessQR / SVD kernels.  The choice depends on (m, n, maxit) only, never on scheduling. */
+int psa_gpu_plan(int m, int n, int maxit, int* warps_per_sm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,7 @@ MATRIX_DEFAULT, MATRIX_UPPER_WRAPPER = 0, 1
 EXPORTS = ("psa_gpu_init", "psa_gpu_set_matrix", "psa_gpu_set_matrix_ex", "psa_gpu_set_matrix_device",
            "psa_gpu_set_thresholds", "psa_gpu_project", "psa_gpu_grid", "psa_gpu_grid_batched", "psa_gpu_grid_device",
            "psa_gpu_postprocess", "psa_gpu_pseudomode", "psa_gpu_apply_resolvent", "psa_gpu_last_stats", "psa_gpu_free",
-           "psa_gpu_strerror", "psa_gpu_last_error", "psa_gpu_version")
+           "psa_gpu_strerror", "psa_gpu_last_error", "psa_gpu_version", "psa_gpu_plan")
 
 _lib = None
 
@@ -75,6 +75,8 @@ def load():
     lib.psa_gpu_last_error.restype = C.c_char_p
     lib.psa_gpu_version.argtypes = []
     lib.psa_gpu_version.restype = C.c_char_p
+    lib.psa_gpu_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    lib.psa_gpu_plan.restype = C.c_int
     _lib = lib
     return lib
 
@@ -254,3 +256,11 @@ class PsaGpu:
 
 def version() -> str:
     return load().psa_gpu_version().decode()
+
+
+def plan(m: int, n: int, maxit: int = 99):
+    """(algo name | None, grid points in flight per SM in the point-resident kernel or 0): which machine a grid call
+    would use for an m x n matrix -- host logic only, works without a GPU."""
+    w = C.c_int(0)
+    algo = load().psa_gpu_plan(int(m), int(n), int(maxit), C.byref(w))
+    return ALGO_NAMES[algo], w.value

@@ -998,6 +998,16 @@ extern "C" {
 
 const char* psa_gpu_version(void) { return "psagpu 0.2.0 sm_100a"; }
 
+int psa_gpu_plan(int m, int n, int maxit, int* warps_per_sm) {
+  if (warps_per_sm) *warps_per_sm = 0;
+  if (m < 1 || n < 1 || maxit < 1 || maxit > HIST_MAX - 2) return PSA_ALGO_NONE;
+  Context defaults;  // the reference's default thresholds
+  const int algo = classify(&defaults, m, n);
+  if (algo == PSA_ALGO_SQ_LANC && warps_per_sm && !getenv("PSA_NO_POINT_KERNEL"))
+    *warps_per_sm = pt_warps(n, std::max(HIST_MIN, (maxit + 2 + 31) / 32 * 32));
+  return algo;
+}
+
 const char* psa_gpu_strerror(int status) {
   switch (status) {
     case PSA_OK: return "ok";

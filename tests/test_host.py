@@ -154,3 +154,23 @@ def test_rows_for_rank_partition(pkg):
         for world in (1, 2, 4, 8):
             rows = np.concatenate([sharding.rows_for_rank(ly, r, world) for r in range(world)])
             assert sorted(rows.tolist()) == list(range(ly))
+
+
+def test_plan_selects_the_machine_from_the_shape_only(pkg):
+    """psa_gpu_plan: the branch of psacore (compute.jl:478, 534, 565, 579, 588-590) and whether a square matrix takes the
+    single-launch point-resident kernel -- host logic, no device.  The documented range: n <= 163 at maxit = 99 (the
+    packed triangle + >= 8 warps' tridiagonals must fit one SM's shared memory), the tick engine above or when the
+    alpha / beta histories of a large maxit no longer fit."""
+    from pseudospectra_jl_b200._lib import plan
+    assert plan(54, 54) == ("SVD", 0) and plan(40, 30) == ("SVD", 0)          # n < minlancs4psa
+    assert plan(55, 55) == ("sq_lanc", 16) and plan(150, 150) == ("sq_lanc", 16)
+    assert plan(155, 155)[1] == 16 and 8 <= plan(160, 160)[1] < 16
+    assert plan(163, 163) == ("sq_lanc", 8) and plan(164, 164) == ("sq_lanc", 0)
+    assert plan(4000, 4000) == ("sq_lanc", 0)
+    assert plan(150, 150, maxit=3)[1] == 16 and plan(150, 150, maxit=400)[1] == 0 and plan(55, 55, maxit=2000)[1] == 0
+    assert plan(201, 200) == ("HessQR", 0) and plan(101, 100) == ("rect_qr", 0)  # m > maxstdqr4hess or not
+    assert plan(300, 200) == (None, 0) and plan(0, 5) == (None, 0) and plan(100, 100, maxit=5000) == (None, 0)
+    # the shared-memory layout the kernel relies on: eight consecutive triangular numbers are distinct mod 8, so a
+    # quarter-warp reading one matrix row out of the packed upper triangle hits eight different 16-byte bank groups
+    tri = [i * (i + 1) // 2 for i in range(512)]
+    assert all(len({t % 8 for t in tri[a:a + 8]}) == 8 for a in range(0, 504, 8))
