@@ -22,6 +22,19 @@ const ALGO = Dict(Cint(1) => :sq_lanc, Cint(2) => :HessQR, Cint(3) => :rect_qr, 
 
 strerror(st) = unsafe_string(ccall((:psa_gpu_strerror, libpsagpu), Cstring, (Cint,), st))
 
+"""
+    plan(m, n, maxit=99) -> (algo::Union{Symbol,Nothing}, points_in_flight_per_sm::Int)
+
+Which machine a grid call would use for an m x n matrix (host logic only, no device needed): the `psacore` branch and,
+for small square matrices, the number of grid points one SM keeps in flight in the single-launch point-resident kernel
+(0: tick engine / HessQR / SVD kernels).
+"""
+function plan(m::Integer, n::Integer, maxit::Integer=99)
+    w = Ref{Cint}(0)
+    a = ccall((:psa_gpu_plan, libpsagpu), Cint, (Cint, Cint, Cint, Ref{Cint}), m, n, maxit, w)
+    return get(ALGO, a, nothing), Int(w[])
+end
+
 mutable struct Context
     ptr::Ptr{Cvoid}
     ngpus::Int
