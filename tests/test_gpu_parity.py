@@ -782,3 +782,17 @@ def test_point_resident_kernel_batched_start_vectors_and_order(pkg, gpu):
         assert _rel(Z[rows], Zc, _floor(T)) < RTOL and np.mean(it[rows] == itc) >= 0.995
     Z2, it2, _, _ = gpu.grid(x, y, qs, row_batch=rb)
     assert np.array_equal(Z, Z2) and np.array_equal(it, it2)
+
+
+@pytest.mark.parametrize("n", [60, 130, 300])
+def test_closed_form_sigma_min(gpu, n):
+    """Known answers that need no oracle: a diagonal matrix (sigma_min = distance to the spectrum) and lambda*I plus one
+    corner entry (2x2 closed form), see tests/test_oracle.py: closed_form_cases.  n = 60, 130 run the point-resident
+    kernel, n = 300 the tensor-core tick engine; the bar is the Lanczos stopping tolerance (compute.jl:658-661)."""
+    from test_oracle import CLOSED_FORM_Z, closed_form_cases
+    q0 = po.start_vector(n, 3)
+    for name, T, exact in closed_form_cases(n):
+        gpu.set_matrix(np.asfortranarray(T))
+        for z in CLOSED_FORM_Z:
+            Z, it, counts, algo = gpu.grid(np.array([z.real]), np.array([z.imag]), q0)
+            assert algo == "sq_lanc" and counts[0] == 0 and abs(Z[0, 0] / exact(z) - 1) < 1e-4, (name, z, Z[0, 0], exact(z))

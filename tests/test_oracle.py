@@ -1,5 +1,6 @@
 """CPU tests: the oracle against dense SVD and the committed golden vectors, the C restatement against the numpy
 one, and the reference's grid-construction rules (src/compute.jl:122-145,270-279; src/utils.jl:112-141,175-191)."""
+import math
 import numpy as np
 import pytest
 
@@ -256,3 +257,41 @@ def test_grcar100_published_values_pin_the_lanczos_oracles():
 
     check_go(numpy_oracle)
     check_go(c_oracle)
+
+
+# ---- closed-form known answers (independent of any implementation) --------------------------------------------------
+def closed_form_cases(n):
+    """(name, upper-triangular T, exact sigma_min(T - zI) as a function of z) for two families with a closed form:
+    a diagonal (normal) matrix -- sigma_min = distance to the spectrum -- and lambda*I plus one corner entry alpha,
+    whose only non-trivial singular pair comes from the 2x2 block [[mu, alpha], [0, mu]], mu = lambda - z:
+    sigma_min^2 = (2|mu|^2 + |alpha|^2 - sqrt((2|mu|^2 + |alpha|^2)^2 - 4|mu|^4)) / 2."""
+    rng = np.random.default_rng(n)
+    d = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    lam, alpha = 0.3 - 0.2j, 2.5 + 1.0j
+    C = lam * np.eye(n, dtype=complex)
+    C[0, n - 1] = alpha
+
+    def corner(z):
+        m2, a2 = abs(lam - z) ** 2, abs(alpha) ** 2
+        s = 2 * m2 + a2
+        return math.sqrt(2 * m2 * m2 / (s + math.sqrt(s * s - 4 * m2 * m2)))  # the same root, without cancellation
+
+    return [("diagonal", np.diag(d), lambda z: float(np.min(np.abs(d - z)))), ("corner", C, corner)]
+
+
+CLOSED_FORM_Z = [0.9 + 0.4j, -1.3 + 0.2j, 0.1 - 2.0j, 2.2 + 1.7j, 0.31 - 0.18j]
+
+
+@pytest.mark.parametrize("n", [60, 130])
+def test_oracles_reproduce_closed_form_sigma_min(n):
+    """Lanczos stops on a 1e-5 relative change of sigma_max of the inverse (compute.jl:658-661), so sigma_min is good to
+    that order; both restatements must land on the closed form."""
+    q0 = po.start_vector(n, 3)
+    for name, T, exact in closed_form_cases(n):
+        T = np.asfortranarray(T)
+        for z in CLOSED_FORM_Z:
+            ref = exact(z)
+            zn = po.psacore(T, q0, np.array([z.real]), np.array([z.imag]), 1)[0][0, 0]
+            zc = co.grid(T, np.array([z.real]), np.array([z.imag]), q0)[0][0, 0]
+            assert abs(zn / ref - 1) < 1e-4 and abs(zc / ref - 1) < 1e-4, (name, z, zn, zc, ref)
+            assert abs(po.sigmin_svd(T, z) / ref - 1) < 1e-10, (name, z)
