@@ -21,7 +21,9 @@ What pins it:
  (iii) the C restatement in oracle/psa_oracle.c (independent triangular solves + Sturm-bisection eigenvalues) and the
        OpenBLAS-worker arm (oracle/blas_arm.py) agreeing with this file to 1e-14;
  (iv)  the reference's own tests at this boundary restated with their tolerance (threads.jl 1e-4; medcplx / medrect /
-       smrect `algo` symbols), and hand-derived known answers for the grid rules (tests/test_host_kat.py).
+       smrect `algo` symbols), and hand-derived known answers for the grid rules (tests/test_host_kat.py);
+ (v)   closed-form sigma_min (a diagonal matrix: distance to the spectrum; lambda*I plus one corner entry: 2x2 closed
+       form), tests/test_oracle.py: closed_form_cases -- implementation-independent known answers.
 """
 from __future__ import annotations
 
