@@ -90,6 +90,35 @@ def start_vector(n, seed=0):
     return q / np.linalg.norm(q)
 
 
+def small_matrix_leg(pkg, device=0, repeat=5):
+    """BASELINE.json configs[0] beside the headline (NOT part of `value`, run after the timed region): the reference's
+    README example, B = diagm(1=>2im, 2=>-1, 3=>2, -2=>-4, -3=>-2im), n = 150 (README.md:40-42), its complex Schur factor,
+    100 x 100 grid on vec2ax(eigenvalues).  Small square matrices take the point-resident kernel (csrc/psa_point.cuh):
+    one launch per grid, zero scheduler ticks.  Reports the device time of one psa_gpu_grid call (best of `repeat`)."""
+    import scipy.linalg as sla
+    n = 150
+    B = np.zeros((n, n), dtype=complex)
+    for k, v in ((1, 2j), (2, -1.0), (3, 2.0), (-2, -4.0), (-3, -2j)):
+        B += np.diag(np.full(n - abs(k), v, dtype=complex), k)
+    T, _ = sla.schur(B, output="complex")
+    T = np.asfortranarray(np.triu(T))
+    ax, x, y = grid_for(T, 100, pkg)
+    q0 = start_vector(n)
+    best, st, counts, algo = None, None, None, None
+    with pkg.PsaGpu(1, [device]) as g:
+        g.set_matrix(T)
+        for _ in range(repeat):
+            _, _, counts, algo = g.grid(x, y, q0)
+            s_ = g.last_stats()
+            if best is None or s_["grid_ms"] < best:
+                best, st = s_["grid_ms"], s_
+    return {"workload": "README 150x150 Schur factor, 100x100 grid (BASELINE.json configs[0])", "algo": algo,
+            "ms_per_grid": best, "points": int(counts[3]), "mean_iters": float(counts[2] / max(counts[3], 1)),
+            "nonconverged": int(counts[0]), "ticks": st["ticks"], "launches": st["total_launches"],
+            "tflops": st["flops"] / (best * 1e9) if best else None,
+            "kernel": "psa::point_lanczos_kernel (one warp per grid point)" if st["ticks"] == 0 else "tick engine"}
+
+
 # ---- clocks -------------------------------------------------------------------------------------------------
 
 class ClockSampler:
@@ -396,6 +425,12 @@ def run_ours(args):
         for _ in range(3):
             ctx.apply_resolvent(z8, Q8)
             lone_ms = ctx.last_stats()["solve_ms"] if lone_ms is None else min(lone_ms, ctx.last_stats()["solve_ms"])
+    small = None
+    if rank == 0:  # configs[0] beside the headline; isolated: a failure here must never cost the headline line
+        try:
+            small = small_matrix_leg(pkg, local_rank)
+        except Exception as e:  # noqa: BLE001
+            small = {"error": repr(e)}
     if rank == 0 and world == 1 and args.dump_iters:
         np.save(args.dump_iters, d_it.t().cpu().numpy())
     if rank == 0:
@@ -442,6 +477,7 @@ def run_ours(args):
                         "fallback": int(counts[1]), "ticks_per_step": stats_acc["ticks"] / args.steps,
                         "lone_panel_solve_ms": lone_ms},
             "schur_s": schur_s, "schur": how, "bcast_s": bcast_s, "algo": state["algo"],
+            "small_matrix": small,
         }
         parity_fail = False
         if world == 1 and not args.no_cpu:
